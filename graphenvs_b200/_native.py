@@ -1,0 +1,119 @@
+"""ctypes binding of libgraphenvs_b200.so (include/graphenvs_b200.h).
+
+There is NO fallback: if the CUDA library is missing or fails to load, importing the engine
+raises.  `build()` compiles it in-tree with nvcc for sm_100a (works without a GPU).
+"""
+import ctypes as C
+import glob
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libgraphenvs_b200.so")
+_SOURCES = sorted(glob.glob(os.path.join(_PKG, "csrc", "*.cu")))
+_HEADERS = sorted(glob.glob(os.path.join(_PKG, "csrc", "*.cuh"))) + [os.path.join(_ROOT, "include", "graphenvs_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in _SOURCES + _HEADERS if os.path.exists(p))
+
+
+def build(force=False, verbose=False):
+    """nvcc -> graphenvs_b200/libgraphenvs_b200.so (sm_100a, -lineinfo)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libgraphenvs_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"),
+                                 "-o", LIB_PATH] + _SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call(cmd, env=env)
+    return LIB_PATH
+
+
+class StepFlags(C.Structure):
+    _fields_ = [("done", C.c_uint8), ("solved", C.c_int8), ("status", C.c_uint8), ("has_mask", C.c_uint8)]
+
+
+_P = C.c_void_p
+
+
+class GeBatch(C.Structure):
+    """Mirror of `struct ge_batch` (include/graphenvs_b200.h) -- keep field order in sync."""
+    _fields_ = [
+        ("kind", C.c_int32), ("B", C.c_int32), ("N", C.c_int32), ("M", C.c_int32),
+        ("parenting", C.c_int32), ("n_dests", C.c_int32), ("n_choices", C.c_int32), ("n_targets", C.c_int32),
+        ("flags", C.c_uint32), ("env_id0", C.c_int32),
+        ("NW", C.c_int32), ("MW", C.c_int32), ("A", C.c_int32), ("AW", C.c_int32), ("AP", C.c_int32),
+        ("RP", C.c_int32), ("MP", C.c_int32), ("ADJS", C.c_int32),
+        ("max_distance", C.c_double),
+        ("row_ptr", _P), ("col", _P), ("w32", _P), ("w64", _P), ("adj_bits", _P),
+        ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
+        ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("features", _P),
+        ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P),
+        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("acc", _P),
+    ]
+
+
+class StepOut(C.Structure):
+    _fields_ = [("reward", _P), ("flags", _P), ("solution_cost", _P)]
+
+
+EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
+           "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_sample_actions", "ge_obs_len",
+           "ge_obs_flat", "ge_step_host", "ge_stats"]
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "graphenvs_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.ge_last_error.restype = C.c_char_p
+    BP = C.POINTER(GeBatch)
+    L.ge_fill_layout.argtypes = [BP]
+    L.ge_step_smem_bytes.argtypes = [BP]
+    L.ge_build_adjacency.argtypes = [BP, _P]
+    L.ge_prepare.argtypes = [BP, C.c_int, _P, _P]
+    L.ge_features.argtypes = [BP, _P]
+    L.ge_generate.argtypes = [BP, C.c_uint64, _P, _P, _P, _P, _P]
+    L.ge_reset.argtypes = [BP, _P, _P]
+    L.ge_step.argtypes = [BP, _P, C.POINTER(StepOut), _P]
+    L.ge_sample_actions.argtypes = [BP, C.c_uint64, C.c_uint32, _P, _P]
+    L.ge_obs_len.argtypes = [BP]
+    L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
+    L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P]
+    L.ge_stats.argtypes = [BP, _P, _P]
+    if L.ge_abi_version() != 1:
+        raise NativeError("ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError("graphenvs_b200 native call failed (%d): %s" % (rc, lib().ge_last_error().decode()))

@@ -1,0 +1,312 @@
+"""BatchedGraphEnv -- the batched vector-env entry point over the CUDA engine.
+
+Per-env semantics are those of the reference's single-instance gymnasium envs
+(graph_envs/<env>.py, see include/graphenvs_b200.h for the line map); B instances of one env
+kind with uniform (n_nodes, n_edges) live on one GPU as CSR + SoA weights + packed bitsets.
+All state tensors are torch tensors on the device and are exposed as zero-copy views.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native
+from .spec import ENV_SPECS, check_ctor_args
+
+PREP_HEURISTIC, PREP_MAXDIST, PREP_INRANGE = 1, 2, 4
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedGraphEnv:
+    def __init__(self, env_id, num_envs, n_nodes, n_edges=-1, *, device=None, byte_mask=True, auto_reset=False,
+                 structural_features=False, env_id0=0, keep_w64=True, **kwargs):
+        self.lib = _native.lib()  # raises when the CUDA library is absent -- no fallback
+        if not torch.cuda.is_available():
+            raise _native.NativeError("graphenvs_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.spec = ENV_SPECS[env_id]
+        self.env_id = env_id
+        self.params = check_ctor_args(env_id, n_nodes, n_edges, kwargs)  # reference ctor rules
+        P = self.params
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.B, self.N, self.E = int(num_envs), int(P["n_nodes"]), int(P["n_edges"])
+        self.M = 2 * self.E
+        self.is_eval_env = bool(P.get("is_eval_env", False))
+        self.structural_features = bool(structural_features)
+        d = _native.GeBatch()
+        d.kind, d.B, d.N, d.M = self.spec.kind, self.B, self.N, self.M
+        d.parenting = int(P.get("parenting", -1))
+        d.n_dests = int(P.get("n_dests", 0))
+        d.n_choices = int(P.get("n_choices", 0))
+        d.n_targets = int(P.get("target_count", 0))
+        d.flags = (1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0)
+        d.env_id0 = int(env_id0)
+        d.max_distance = float(P.get("max_distance", 0.0)) if env_id == "DistributionCenter-v0" else 0.0
+        _native.check(self.lib.ge_fill_layout(C.byref(d)))
+        self.desc = d
+        self.F = self.spec.node_f + 5
+        self.Fe = self.spec.edge_f
+        self.obs_len = self.N * self.F + self.M * self.Fe + 2 * self.M
+
+        dev, B, N = self.device, self.B, self.N
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        self.t = {}
+        T = self.t
+        T["row_ptr"] = z((B, d.RP), torch.int32)
+        T["col"] = z((B, d.MP), torch.int32)
+        if self.spec.step_w == "f32":
+            T["w32"] = z((B, d.MP), torch.float32)
+        if self.spec.step_w == "f64" or (keep_w64 and self.spec.step_w == "f32"):
+            T["w64"] = z((B, d.MP), torch.float64)
+        if self.spec.uses_adj:
+            T["adj_bits"] = z((B, d.ADJS), torch.int32)
+        T["src"] = z((B,), torch.int32)
+        T["dest"] = z((B,), torch.int32)
+        if self.spec.has_targets:
+            T["target_bits"] = z((B, d.NW), torch.int32)
+        if self.spec.has_node_cost:
+            T["node_cost"] = z((B, N), torch.float32)
+        if P.get("spatial"):
+            T["node_xy"] = z((B, N, 2), torch.float32)
+        if env_id == "MulticastRouting-v0":
+            T["max_dist32"] = z((B,), torch.float32)
+            T["edge_bits"] = z((B, d.MW), torch.int32)
+            T["dist32"] = z((B, N), torch.float32)
+        if env_id == "DistributionCenter-v0":
+            T["targets"] = z((B, max(d.n_targets, 1)), torch.int32)
+            T["in_range"] = z((B, max(d.n_targets, 1), d.NW), torch.int32)
+        T["heuristic"] = z((B,), torch.float64)
+        if self.structural_features:
+            T["features"] = z((B, N, 5), torch.float32)
+        T["head"] = z((B,), torch.int32)
+        T["node_bits"] = z((B, d.NW), torch.int32)
+        if env_id in ("DistributionCenter-v0", "DensestSubgraph-v0"):
+            T["node_bits2"] = z((B, d.NW), torch.int32)
+        T["cost"] = z((B,), torch.float64)
+        T["counters"] = z((B, 4), torch.int32)
+        T["done"] = z((B,), torch.uint8)
+        T["mask_bits"] = z((B, d.AW), torch.int32)
+        if byte_mask:
+            T["mask_bytes"] = z((B, d.AP), torch.uint8)
+        T["acc"] = z((B, 4), torch.float64)
+        # step outputs
+        self.reward = z((B,), torch.float32)
+        self.flags = z((B, 4), torch.uint8)
+        self.solution_cost = z((B,), torch.float64)
+        self.actions_dev = z((B,), torch.int32)
+        self._stats = z((4,), torch.float64)
+        self._sync_desc()
+        self._out = _native.StepOut(_ptr(self.reward), _ptr(self.flags), _ptr(self.solution_cost))
+        self._loaded = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_desc(self):
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "src", "dest", "target_bits", "node_cost", "node_xy",
+                     "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
+                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc"):
+            t = self.t.get(name)
+            setattr(self.desc, name, t.data_ptr() if t is not None else None)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def memory_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+    def release_w64(self):
+        """Drop the float64 weights of kinds that step in float32 (after prepare)."""
+        if self.spec.step_w == "f32" and "w64" in self.t:
+            del self.t["w64"]
+            self._sync_desc()
+
+    # ------------------------------------------------------------------ instance loading
+    def load_instances(self, instances, prepare=True):
+        """instances: list of B `Instance`s (graphenvs_b200.instances) -- host data, reference edge order."""
+        assert len(instances) == self.B, "need exactly num_envs instances"
+        d, B, N, M = self.desc, self.B, self.N, self.M
+        row_ptr = np.zeros((B, d.RP), np.int32)
+        col = np.zeros((B, d.MP), np.int32)
+        w64 = np.zeros((B, d.MP), np.float64)
+        src = np.zeros(B, np.int32)
+        dest = np.zeros(B, np.int32)
+        tbits = np.zeros((B, d.NW), np.uint32)
+        ncost = np.zeros((B, N), np.float32)
+        nxy = np.zeros((B, N, 2), np.float32)
+        maxd = np.zeros(B, np.float32)
+        targets = np.zeros((B, max(d.n_targets, 1)), np.int32)
+        heur = np.zeros(B, np.float64)
+        have_heur = True
+        for b, ins in enumerate(instances):
+            links = np.asarray(ins.links, dtype=np.int64).reshape(-1, 2)
+            assert ins.n_nodes == N and links.shape[0] == M, "instance shape mismatch"
+            s = links[:, 0]
+            assert np.all(s[1:] >= s[:-1]), "edge_links must be source-sorted (reference order)"
+            row_ptr[b, 1:N + 1] = np.cumsum(np.bincount(s, minlength=N))
+            if self.spec.action_type == "edge":
+                assert np.all(np.diff(row_ptr[b, :N + 1]) > 0), "edge-action envs need every node to have degree >= 1"
+            col[b, :M] = links[:, 1]
+            w64[b, :M] = ins.w64
+            src[b], dest[b] = ins.src, ins.dest
+            if self.spec.has_targets and ins.dests is not None:
+                for t in np.asarray(ins.dests).ravel():
+                    tbits[b, t >> 5] |= np.uint32(1 << (int(t) & 31))
+                if self.env_id == "DistributionCenter-v0":
+                    tl = np.asarray(ins.dests, dtype=np.int32).ravel()
+                    assert tl.shape[0] == d.n_targets
+                    targets[b, :d.n_targets] = tl
+            if ins.node_cost is not None:
+                ncost[b] = np.asarray(ins.node_cost, dtype=np.float64).astype(np.float32)
+            if ins.node_xy is not None:
+                nxy[b] = np.asarray(ins.node_xy, dtype=np.float64).astype(np.float32)
+            if ins.max_distance is not None:
+                maxd[b] = np.float32(ins.max_distance)
+            if ins.heuristic is None:
+                have_heur = False
+            else:
+                heur[b] = ins.heuristic
+        T, dev = self.t, self.device
+        up = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+        T["row_ptr"].copy_(up(row_ptr))
+        T["col"].copy_(up(col))
+        if "w64" in T:
+            T["w64"].copy_(up(w64))
+        if "w32" in T:
+            T["w32"].copy_(up(w64.astype(np.float32)))
+        T["src"].copy_(up(src))
+        T["dest"].copy_(up(dest))
+        if "target_bits" in T:
+            T["target_bits"].copy_(up(tbits.view(np.int32)))
+        if "node_cost" in T:
+            T["node_cost"].copy_(up(ncost))
+        if "node_xy" in T:
+            T["node_xy"].copy_(up(nxy))
+        if "max_dist32" in T:
+            T["max_dist32"].copy_(up(maxd))
+        if "targets" in T:
+            T["targets"].copy_(up(targets))
+        if have_heur:
+            T["heuristic"].copy_(up(heur))
+        feats = [ins.features for ins in instances]
+        if self.structural_features and all(f is not None for f in feats):
+            T["features"].copy_(up(np.stack([np.asarray(f, dtype=np.float32) for f in feats])))
+            self._features_loaded = True
+        else:
+            self._features_loaded = False
+        self.finalize_graphs(prepare=prepare, heuristics=self.is_eval_env and not have_heur)
+
+    def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None):
+        """Derived static data after the CSR arrays are in place (load_instances / generate)."""
+        L, d = self.lib, self.desc
+        if self.spec.uses_adj:
+            _native.check(L.ge_build_adjacency(C.byref(d), self._stream()))
+        what = 0
+        if prepare and self.env_id == "DistributionCenter-v0" and d.parenting == 2:
+            what |= PREP_INRANGE
+        if heuristics and self.spec.heuristic_on_device(self.params):
+            what |= PREP_HEURISTIC
+        if u01 is not None and self.env_id == "MulticastRouting-v0":
+            what |= PREP_MAXDIST
+        if what:
+            _native.check(L.ge_prepare(C.byref(d), what, _ptr(u01), self._stream()))
+        if features is None:
+            features = self.structural_features and not getattr(self, "_features_loaded", False)
+        if features:
+            _native.check(L.ge_features(C.byref(d), self._stream()))
+        self._loaded = True
+
+    def generate(self, seed=0):
+        """Device-side instance generation (distribution parity with the reference's reset())."""
+        L, d, T = self.lib, self.desc, self.t
+        w64 = T.get("w64")
+        tmp64 = None
+        if w64 is None:
+            tmp64 = torch.zeros((self.B, d.MP), dtype=torch.float64, device=self.device)
+            w64 = tmp64
+            d.w64 = w64.data_ptr()
+        _native.check(L.ge_generate(C.byref(d), int(seed), _ptr(T["row_ptr"]), _ptr(T["col"]), _ptr(w64),
+                                    _ptr(T.get("w32")), self._stream()))
+        u01 = None
+        if self.env_id == "MulticastRouting-v0":
+            g = torch.Generator(device=self.device)
+            g.manual_seed(int(seed) + 12345 + d.env_id0)
+            u01 = torch.rand((self.B,), dtype=torch.float64, device=self.device, generator=g)
+        self.finalize_graphs(prepare=True, heuristics=self.is_eval_env, u01=u01)
+        if tmp64 is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+            self._sync_desc()
+
+    # ------------------------------------------------------------------ hot path
+    def reset(self, select=None):
+        """State init + first mask for all envs (or those with select[b] != 0)."""
+        assert self._loaded, "load_instances() or generate() first"
+        sel = None
+        if select is not None:
+            sel = select.to(device=self.device, dtype=torch.uint8).contiguous()
+        _native.check(self.lib.ge_reset(C.byref(self.desc), _ptr(sel), self._stream()))
+        return self.info()
+
+    def step(self, actions):
+        """actions: int32[B] on the device.  Returns (reward f32[B], done bool[B], info)."""
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        _native.check(self.lib.ge_step(C.byref(self.desc), _ptr(actions), C.byref(self._out), self._stream()))
+        return self.reward, self.flags[:, 0].bool(), self.info(step=True)
+
+    def step_async(self, actions):
+        """Same as step() without building the info dict (bench / rollout loops)."""
+        _native.check(self.lib.ge_step(C.byref(self.desc), _ptr(actions), C.byref(self._out), self._stream()))
+
+    def sample_actions(self, seed, t, out=None):
+        out = self.actions_dev if out is None else out
+        _native.check(self.lib.ge_sample_actions(C.byref(self.desc), int(seed), int(t), _ptr(out), self._stream()))
+        return out
+
+    def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None):
+        """End-to-end C-ABI call with HOST (pinned) buffers: H2D actions, step, D2H results, sync."""
+        _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev),
+                                            C.byref(self._out), _ptr(h_reward), _ptr(h_flags), _ptr(h_cost),
+                                            _ptr(h_mask), self._stream()))
+
+    def info(self, step=False):
+        d = {"mask": self.mask, "mask_bits": self.t["mask_bits"], "heuristic_solution": self.t["heuristic"]}
+        if step:
+            f = self.flags
+            d.update(solved=f[:, 1].view(torch.int8), status=f[:, 2], has_mask=f[:, 3].bool(),
+                     solution_cost=self.solution_cost)
+        return d
+
+    @property
+    def mask(self):
+        """bool[B, A] view of the current valid-action masks (None when byte_mask=False)."""
+        mb = self.t.get("mask_bytes")
+        return None if mb is None else mb[:, :self.desc.A].view(torch.bool)
+
+    def obs_flat(self, env_lo=0, count=None):
+        """Reference wire format (utils.vectorize_graph): float32[count, obs_len]."""
+        count = self.B - env_lo if count is None else count
+        out = torch.empty((count, self.obs_len), dtype=torch.float32, device=self.device)
+        _native.check(self.lib.ge_obs_flat(C.byref(self.desc), int(env_lo), int(count), _ptr(out), self._stream()))
+        return out
+
+    def compute_features(self):
+        if "features" not in self.t:
+            self.t["features"] = torch.zeros((self.B, self.N, 5), dtype=torch.float32, device=self.device)
+            self.structural_features = True
+            self._sync_desc()
+        _native.check(self.lib.ge_features(C.byref(self.desc), self._stream()))
+        return self.t["features"]
+
+    def stats(self):
+        """Device-side reduction of the per-env accumulators: episodes, solved, sum reward, sum final cost."""
+        _native.check(self.lib.ge_stats(C.byref(self.desc), _ptr(self._stats), self._stream()))
+        return self._stats
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.t.items()}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            self.t[k].copy_(v)

@@ -1,0 +1,514 @@
+// ge_api.cu -- kernels + extern "C" entry points of libgraphenvs_b200.so (sm_100a).
+// See include/graphenvs_b200.h for the ABI and the reference interfaces each call replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ge_envs.cuh"
+
+using namespace ge;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define GE_CUDA_OK(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) return fail(GE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+__host__ __device__ static inline bool is_edge_kind(int kind) { return kind == GE_STEINER_TREE || kind == GE_MULTICAST_ROUTING; }
+static bool uses_adj(int kind) {
+    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_DENSEST_SUBGRAPH;
+}
+
+// ------------------------------------------------------------------ kernels
+namespace {
+
+__global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int32_t *__restrict__ actions, ge_step_out out,
+                                                         int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    EnvPtrs p = env_ptrs(d, b);
+    StepRes r;
+    if (d.done[b]) {  // only reachable with auto-reset off
+        r.reward = 0.0; r.sol = __longlong_as_double(0x7ff8000000000000ll);
+        r.done = 0; r.solved = -1; r.has_mask = 0; r.status = GE_STEP_AFTER_DONE;
+    } else {
+        step_env(d, p, s, lane, b, actions[b], r);
+    }
+    if (lane == 0) {
+        out.reward[b] = (float)r.reward;
+        ge_step_flags f;
+        f.done = (uint8_t)r.done; f.solved = (int8_t)r.solved; f.status = (uint8_t)r.status; f.has_mask = (uint8_t)r.has_mask;
+        out.flags[b] = f;
+        out.solution_cost[b] = r.sol;
+        if (r.status == GE_STEP_OK) {
+            double *acc = d.acc + (size_t)b * 4;
+            acc[2] += r.reward;
+            if (r.done) {
+                acc[0] += 1.0;
+                if (r.solved == 1) acc[1] += 1.0;
+                if (r.sol == r.sol) acc[3] += r.sol;
+            }
+        }
+    }
+    if (r.done && (d.flags & GE_FLAG_AUTO_RESET)) {
+        __syncwarp();
+        reset_env(d, p, s, lane, b);
+    }
+}
+
+__global__ void __launch_bounds__(GE_WPB * 32) reset_kernel(ge_batch d, const uint8_t *__restrict__ select, int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    if (select && !select[b]) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    EnvPtrs p = env_ptrs(d, b);
+    reset_env(d, p, s, lane, b);
+}
+
+// Uniform choice among the valid mask bits (README.md:54-68 loop), counter-based RNG.
+__global__ void __launch_bounds__(GE_WPB * 32) sample_kernel(ge_batch d, uint64_t seed, uint32_t t, int32_t *__restrict__ actions) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    const uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
+    int total = 0;
+    for (int w = lane; w < d.AW; w += 32) total += __popc(mb[w]);
+    total = __reduce_add_sync(GE_FULL, total);
+    int action = -1;
+    if (total > 0) {
+        uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t) * (uint64_t)total) >> 32);
+        int before = 0;
+        for (int w0 = 0; w0 < d.AW; w0 += 32) {
+            int w = w0 + lane;
+            uint32_t word = w < d.AW ? mb[w] : 0u;
+            int c = __popc(word), inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int x = __shfl_up_sync(GE_FULL, inc, o);
+                if (lane >= o) inc += x;
+            }
+            int chunk = __shfl_sync(GE_FULL, inc, 31);
+            if ((int)r < before + chunk) {
+                unsigned hit = __ballot_sync(GE_FULL, (int)r < before + inc);
+                int src_lane = __ffs(hit) - 1;
+                int excl = before + inc - c;
+                int pos = (lane == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
+                pos = __shfl_sync(GE_FULL, pos, src_lane);
+                action = ((w0 + src_lane) << 5) + pos;
+                break;
+            }
+            before += chunk;
+        }
+    }
+    if (lane == 0) actions[b] = action;
+}
+
+// adjacency bit-matrix from CSR (load time).
+__global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    for (int i = lane; i < d.ADJS; i += 32) adj[i] = 0;
+    __syncwarp();
+    __threadfence_block();
+    for (int u = lane; u < d.N; u += 32)
+        for (int e = rp[u]; e < rp[u + 1]; ++e) {
+            int c = col[e];
+            atomicOr(&adj[(size_t)u * d.NW + (c >> 5)], 1u << (c & 31));
+        }
+}
+
+// Reference wire format (utils.py:87-88): [nodes.ravel | edges.ravel | edge_links.ravel] float32.
+__global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float *__restrict__ out, int L) {
+    const int b = env_lo + blockIdx.x;
+    float *o = out + (size_t)blockIdx.x * L;
+    const int N = d.N, M = d.M, kind = d.kind;
+    int dyn;
+    switch (kind) {
+    case GE_TSP: case GE_MULTICAST_ROUTING: dyn = 4; break;
+    case GE_DENSEST_SUBGRAPH: dyn = 1; break;
+    case GE_DISTRIBUTION_CENTER: dyn = 5; break;
+    default: dyn = 2;
+    }
+    const int F = dyn + 5, Fe = is_edge_kind(kind) ? 2 : 1;
+    const uint32_t *vis = d.node_bits + (size_t)b * d.NW;
+    const uint32_t *aux = d.node_bits2 ? d.node_bits2 + (size_t)b * d.NW : nullptr;
+    const uint32_t *tgt = d.target_bits ? d.target_bits + (size_t)b * d.NW : nullptr;
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    const int NF = N * F, MF = M * Fe;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        float val = 0.f;
+        if (i < NF) {
+            int v = i / F, c = i - v * F;
+            bool bit = (vis[v >> 5] >> (v & 31)) & 1u;
+            if (c >= dyn) val = d.features ? d.features[((size_t)b * N + v) * 5 + (c - dyn)] : 0.f;
+            else switch (kind) {
+            case GE_SHORTEST_PATH: val = c == 0 ? (float)bit : (float)(v == d.dest[b]); break;
+            case GE_LONGEST_PATH:
+                if (c == 0) val = (float)bit;
+                else val = (v == d.dest[b]) ? 1.f : ((d.parenting == 0 && v == d.src[b]) ? 2.f : 0.f);
+                break;
+            case GE_STEINER_TREE: val = c == 0 ? (float)bit : (float)((tgt[v >> 5] >> (v & 31)) & 1u); break;
+            case GE_TSP:
+                if (c == 0) val = (float)bit;
+                else if (c == 1) val = (float)(v == 0);
+                else val = d.node_xy ? d.node_xy[((size_t)b * N + v) * 2 + (c - 2)] : 0.f;
+                break;
+            case GE_MAX_INDEPENDENT_SET: val = c == 0 ? d.node_cost[(size_t)b * N + v] : (float)bit; break;
+            case GE_DENSEST_SUBGRAPH: val = (float)bit; break;
+            case GE_MULTICAST_ROUTING:
+                if (c == 0) val = (float)bit;
+                else if (c == 1) val = (float)((tgt[v >> 5] >> (v & 31)) & 1u);
+                else if (c == 2) val = d.max_dist32[b];
+                else val = d.dist32[(size_t)b * N + v];
+                break;
+            case GE_DISTRIBUTION_CENTER:
+                if (c == 0) val = d.node_cost[(size_t)b * N + v];
+                else if (c == 1) val = (float)bit;
+                else if (c == 2) val = (float)((tgt[v >> 5] >> (v & 31)) & 1u);
+                else if (c == 3) val = (float)((aux[v >> 5] >> (v & 31)) & 1u);
+                else val = (float)d.max_distance;
+                break;
+            }
+        } else if (i < NF + MF) {
+            int j = i - NF, e = j / Fe, c = j - e * Fe;
+            if (c == 0) {
+                if (kind == GE_MAX_INDEPENDENT_SET || kind == GE_DENSEST_SUBGRAPH) val = 1.f;
+                else val = d.w32 ? d.w32[(size_t)b * d.MP + e] : (float)d.w64[(size_t)b * d.MP + e];
+            } else {
+                val = (kind == GE_MULTICAST_ROUTING) ? (float)((d.edge_bits[(size_t)b * d.MW + (e >> 5)] >> (e & 31)) & 1u) : 0.f;
+            }
+        } else {
+            int j = i - NF - MF, e = j >> 1;
+            val = (j & 1) ? (float)col[e] : (float)edge_src(rp, N, e);
+        }
+        o[i] = val;
+    }
+}
+
+// ---- reset-time derived data ---------------------------------------------------------------
+// SSSP from src: heuristics (shortest_path.py:90, longest_path.py:105, steiner_tree.py:79) and the
+// Multicast max_distance draw (multicast_routing.py:98-103) given the reference's U(0,1) sample.
+__global__ void __launch_bounds__(GE_WPB * 32) prep_sssp_kernel(ge_batch d, int what, const double *__restrict__ u01, int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    int src = (d.kind == GE_MULTICAST_ROUTING) ? 0 : d.src[b];
+    sssp_warp(d, b, lane, s, src, 0.0, false);
+    __syncwarp();
+    if (d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH) {
+        if (lane == 0 && (what & 1)) {
+            double v = __longlong_as_double((long long)s.q[d.dest[b]]);
+            d.heuristic[b] = d.kind == GE_LONGEST_PATH ? -v : v;
+        }
+    } else if (d.kind == GE_STEINER_TREE) {  // n_dests == 1: the single target
+        if (what & 1) {
+            const uint32_t *tg = d.target_bits + (size_t)b * d.NW;
+            int first = 0x7fffffff;
+            for (int w = lane; w < d.NW; w += 32)
+                if (tg[w]) first = min(first, (w << 5) + __ffs(tg[w]) - 1);
+            first = __reduce_min_sync(GE_FULL, first);
+            if (lane == 0) d.heuristic[b] = __longlong_as_double((long long)s.q[first]);
+        }
+    } else if (d.kind == GE_MULTICAST_ROUTING) {
+        if (what & 2) {
+            const uint32_t *tg = d.target_bits + (size_t)b * d.NW;
+            double far_node = 0.0, far_tgt = 0.0;
+            for (int v = lane; v < d.N; v += 32) {
+                double dv = __longlong_as_double((long long)s.q[v]);
+                far_node = fmax(far_node, dv);
+                if ((tg[v >> 5] >> (v & 31)) & 1u) far_tgt = fmax(far_tgt, dv);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                far_node = fmax(far_node, __shfl_xor_sync(GE_FULL, far_node, o));
+                far_tgt = fmax(far_tgt, __shfl_xor_sync(GE_FULL, far_tgt, o));
+            }
+            if (lane == 0) {
+                double md = __dadd_rn(__dmul_rn(u01[b], __dsub_rn(far_node, far_tgt)), far_tgt);
+                d.max_dist32[b] = (float)md;
+            }
+        }
+    }
+}
+
+// MST total weight (steiner_tree.py:81): Prim in fp64; the multiset of MST weights is
+// tie-independent, the sum is compared within 1e-5 (summation order differs from Kruskal's).
+__global__ void __launch_bounds__(GE_WPB * 32) prep_mst_kernel(ge_batch d, int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    EnvPtrs p = env_ptrs(d, b);
+    const u64 INF = 0x7ff0000000000000ull;
+    for (int v = lane; v < d.N; v += 32) s.q[v] = INF;
+    for (int w = lane; w < d.NW; w += 32) s.t0[w] = 0;  // in-tree set
+    __syncwarp();
+    if (lane == 0) s.q[0] = 0ull;
+    __syncwarp();
+    double total = 0.0;
+    for (int it = 0; it < d.N; ++it) {
+        u64 best = ~0ull;  // (key bits, node) packed: keys are non-negative doubles -> order preserving
+        int bestv = -1;
+        for (int v = lane; v < d.N; v += 32)
+            if (!tbit(s.t0, v) && s.q[v] < best) { best = s.q[v]; bestv = v; }
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 ob = __shfl_xor_sync(GE_FULL, best, o);
+            int ov = __shfl_xor_sync(GE_FULL, bestv, o);
+            if (ob < best || (ob == best && ov >= 0 && (bestv < 0 || ov < bestv))) { best = ob; bestv = ov; }
+        }
+        if (bestv < 0 || best == INF) break;  // disconnected remainder
+        total += __longlong_as_double((long long)best);
+        if (lane == 0) s.t0[bestv >> 5] |= 1u << (bestv & 31);
+        __syncwarp();
+        int lo = p.rp[bestv], hi = p.rp[bestv + 1];
+        for (int e = lo + lane; e < hi; e += 32) {
+            int v = p.col[e];
+            if (!tbit(s.t0, v)) atomicMin(&s.q[v], (u64)__double_as_longlong(p.w64[e]));
+        }
+        __syncwarp();
+    }
+    if (lane == 0) d.heuristic[b] = total;
+}
+
+// DistributionCenter in-range tables (distribution_center.py:113-116): one warp per (env, target).
+__global__ void __launch_bounds__(GE_WPB * 32) prep_inrange_kernel(ge_batch d, int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long job = (long long)blockIdx.x * GE_WPB + warp;
+    if (job >= (long long)d.B * d.n_targets) return;
+    const int b = (int)(job / d.n_targets), t = (int)(job % d.n_targets);
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    int node = d.targets[(size_t)b * d.n_targets + t];
+    sssp_warp(d, b, lane, s, node, d.max_distance, true);
+    __syncwarp();
+    uint32_t *row = d.in_range + ((size_t)b * d.n_targets + t) * d.NW;
+    for (int w = lane; w < d.NW; w += 32) {
+        uint32_t bits = 0;
+        for (int j = 0; j < 32; ++j) {
+            int v = (w << 5) + j;
+            if (v < d.N && s.q[v] != 0x7ff0000000000000ull) bits |= 1u << j;
+        }
+        row[w] = bits;
+    }
+}
+
+__global__ void stats_kernel(ge_batch d, double *out4) {
+    __shared__ double sh[4][32];
+    double a[4] = {0, 0, 0, 0};
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < d.B; b += gridDim.x * blockDim.x)
+        for (int k = 0; k < 4; ++k) a[k] += d.acc[(size_t)b * 4 + k];
+    for (int k = 0; k < 4; ++k)
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(GE_FULL, a[k], o);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) for (int k = 0; k < 4; ++k) sh[k][warp] = a[k];
+    __syncthreads();
+    if (warp == 0) {
+        for (int k = 0; k < 4; ++k) {
+            double v = lane < (int)(blockDim.x >> 5) ? sh[k][lane] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GE_FULL, v, o);
+            if (lane == 0) atomicAdd(&out4[k], v);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+static int check_batch(const ge_batch *d) {
+    if (!d) return fail(GE_ERR_ARG, "null batch");
+    if (d->kind < 0 || d->kind > 7) return fail(GE_ERR_ARG, "unknown kind %d", d->kind);
+    if (d->B <= 0 || d->N < 2 || d->M < 0) return fail(GE_ERR_ARG, "bad shape B=%d N=%d M=%d", d->B, d->N, d->M);
+    if (d->N > 4096) return fail(GE_ERR_UNSUPPORTED, "N=%d > 4096 not supported", d->N);
+    if (d->NW != (d->N + 31) / 32 || d->MW != (d->M + 31) / 32) return fail(GE_ERR_ARG, "layout not filled (call ge_fill_layout)");
+    return GE_OK;
+}
+
+static int launch_cfg(const ge_batch *d, int jobs, int *blocks, int *wpw, size_t *smem) {
+    *wpw = scratch_words(*d);
+    *smem = (size_t)(*wpw) * GE_WPB * sizeof(uint32_t);
+    *blocks = (jobs + GE_WPB - 1) / GE_WPB;
+    if (*smem > 227 * 1024) return fail(GE_ERR_UNSUPPORTED, "graph too large for per-warp shared scratch (%zu bytes)", *smem);
+    return GE_OK;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) GE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return GE_OK;
+}
+
+extern "C" {
+
+int ge_abi_version(void) { return GE_ABI_VERSION; }
+const char *ge_last_error(void) { return g_err; }
+
+int ge_fill_layout(ge_batch *d) {
+    if (!d) return fail(GE_ERR_ARG, "null batch");
+    d->NW = (d->N + 31) / 32;
+    d->MW = (d->M + 31) / 32;
+    d->A = is_edge_kind(d->kind) ? d->M : d->N;
+    d->AW = (d->A + 31) / 32;
+    d->AP = (d->A + 15) & ~15;
+    d->RP = (d->N + 1 + 3) & ~3;
+    d->MP = (d->M + 3) & ~3;
+    if (d->MP == 0) d->MP = 4;
+    d->ADJS = (d->N * d->NW + 3) & ~3;
+    return GE_OK;
+}
+
+int ge_step_smem_bytes(const ge_batch *d) { return scratch_words(*d) * GE_WPB * (int)sizeof(uint32_t); }
+
+int ge_build_adjacency(const ge_batch *d, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (!d->adj_bits) return fail(GE_ERR_ARG, "adj_bits is null");
+    adjacency_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, 0, (cudaStream_t)stream>>>(*d);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    int blocks, wpw;
+    size_t smem;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((what & 3) && !d->w64) return fail(GE_ERR_ARG, "ge_prepare needs w64");
+    if (what & 1) {
+        bool sssp = d->kind == GE_SHORTEST_PATH || d->kind == GE_LONGEST_PATH || (d->kind == GE_STEINER_TREE && d->n_dests == 1);
+        bool mst = d->kind == GE_STEINER_TREE && d->n_dests == d->N - 1;
+        if (sssp) {
+            if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+            if ((rc = set_smem(prep_sssp_kernel, smem))) return rc;
+            prep_sssp_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, 1, nullptr, wpw);
+        } else if (mst) {
+            if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+            if ((rc = set_smem(prep_mst_kernel, smem))) return rc;
+            prep_mst_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, wpw);
+        } else if (d->kind == GE_STEINER_TREE || d->kind == GE_TSP || d->kind == GE_MULTICAST_ROUTING) {
+            return fail(GE_ERR_UNSUPPORTED, "tie-dependent eval heuristic (Kou / Christofides / union-of-paths) is not provided; see DESIGN.md");
+        }
+        GE_CUDA_OK(cudaGetLastError());
+    }
+    if ((what & 2) && d->kind == GE_MULTICAST_ROUTING) {
+        if (!u01) return fail(GE_ERR_ARG, "u01 required for Multicast max_distance");
+        if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+        if ((rc = set_smem(prep_sssp_kernel, smem))) return rc;
+        prep_sssp_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, 2, u01, wpw);
+        GE_CUDA_OK(cudaGetLastError());
+    }
+    if ((what & 4) && d->kind == GE_DISTRIBUTION_CENTER && d->n_targets > 0) {
+        if (!d->w64) return fail(GE_ERR_ARG, "in-range tables need w64");
+        long long jobs = (long long)d->B * d->n_targets;
+        if (jobs > 0x7fffffffLL * GE_WPB) return fail(GE_ERR_UNSUPPORTED, "too many (env,target) jobs");
+        wpw = scratch_words(*d);
+        smem = (size_t)wpw * GE_WPB * sizeof(uint32_t);
+        if ((rc = set_smem(prep_inrange_kernel, smem))) return rc;
+        prep_inrange_kernel<<<(unsigned)((jobs + GE_WPB - 1) / GE_WPB), GE_WPB * 32, smem, st>>>(*d, wpw);
+        GE_CUDA_OK(cudaGetLastError());
+    }
+    return GE_OK;
+}
+
+int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
+    int blocks, wpw;
+    size_t smem;
+    if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+    if ((rc = set_smem(reset_kernel, smem))) return rc;
+    reset_kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, select, wpw);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
+    int blocks, wpw;
+    size_t smem;
+    if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+    if ((rc = set_smem(step_kernel, smem))) return rc;
+    step_kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_sample_actions(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    sample_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, 0, (cudaStream_t)stream>>>(*d, seed, t, actions);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_obs_len(const ge_batch *d) {
+    int dyn = (d->kind == GE_TSP || d->kind == GE_MULTICAST_ROUTING) ? 4 : d->kind == GE_DENSEST_SUBGRAPH ? 1 : d->kind == GE_DISTRIBUTION_CENTER ? 5 : 2;
+    int Fe = is_edge_kind(d->kind) ? 2 : 1;
+    return d->N * (dyn + 5) + d->M * Fe + 2 * d->M;
+}
+
+int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
+    obs_kernel<<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d));
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                 ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * (size_t)d->B, cudaMemcpyHostToDevice, st));
+    int rc = ge_step(d, d_actions, out, stream);
+    if (rc) return rc;
+    GE_CUDA_OK(cudaMemcpyAsync(h_reward, out->reward, sizeof(float) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
+    GE_CUDA_OK(cudaMemcpyAsync(h_flags, out->flags, sizeof(ge_step_flags) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
+    if (h_solution_cost)
+        GE_CUDA_OK(cudaMemcpyAsync(h_solution_cost, out->solution_cost, sizeof(double) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
+    if (h_mask) {
+        if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+        GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, (size_t)d->B * d->AP, cudaMemcpyDeviceToHost, st));
+    }
+    GE_CUDA_OK(cudaStreamSynchronize(st));
+    return GE_OK;
+}
+
+int ge_stats(const ge_batch *d, double *out4, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    GE_CUDA_OK(cudaMemsetAsync(out4, 0, sizeof(double) * 4, st));
+    int blocks = (d->B + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    stats_kernel<<<blocks, 256, 0, st>>>(*d, out4);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// ge_common.cuh -- shared device helpers of the graphenvs_b200 engine (sm_100a).
+//
+// Execution shape: ONE WARP PER ENVIRONMENT.  Every env-level quantity (head, done, reward...)
+// is warp-uniform; node/edge sets are packed bitsets (one 32-bit word per lane where possible),
+// staged in a per-warp slice of dynamic shared memory; warp votes / REDUX do the set algebra.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "graphenvs_b200.h"
+
+#define GE_FULL 0xffffffffu
+#define GE_WPB 8  // warps (= environments) per thread block
+
+namespace ge {
+
+typedef unsigned long long u64;
+
+// Per-warp shared-memory scratch.
+struct Scr {
+    u64 *q;         // [N]  fp64 distances as ordered bit patterns / (dist32,edge) keys
+    uint32_t *vis;  // [NW] HAS_MSG / TAKEN
+    uint32_t *aux;  // [NW] second node set (covered, neighbour-union, residual ...)
+    uint32_t *t0, *t1, *t2, *t3;  // [NW] temporaries (frontier / next / reach / candidates)
+    uint32_t *msk;  // [AW] mask under construction
+};
+
+__host__ __device__ inline int scratch_words(const ge_batch &d) {
+    int w = 2 * d.N + 6 * d.NW + d.AW;
+    return (w + 3) & ~3;  // keep every warp slice 16-byte aligned
+}
+
+__device__ inline Scr carve(uint32_t *base, const ge_batch &d) {
+    Scr s;
+    s.q = reinterpret_cast<u64 *>(base);
+    uint32_t *p = base + 2 * d.N;
+    s.vis = p; p += d.NW;
+    s.aux = p; p += d.NW;
+    s.t0 = p; p += d.NW;
+    s.t1 = p; p += d.NW;
+    s.t2 = p; p += d.NW;
+    s.t3 = p; p += d.NW;
+    s.msk = p;
+    return s;
+}
+
+__device__ inline bool tbit(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+__device__ inline uint32_t tail_mask(int n, int w) {  // valid-bit mask of word w of an n-bit set
+    int rem = n - (w << 5);
+    return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+__device__ inline uint32_t expand4(uint32_t b) {  // 4 mask bits -> 4 bytes of 0/1
+    return ((b & 0xfu) * 0x00204081u) & 0x01010101u;
+}
+
+// Counter-based RNG shared bit-for-bit with oracle/graphenvs_oracle.c (ge_mix).
+__host__ __device__ inline uint32_t mix32(uint64_t seed, uint32_t env, uint32_t t) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)env * 0x100000001ull + (((uint64_t)t) << 32 | 0x5bd1e995u));
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
+// Publishes the mask built in shared memory: packed words, optional byte mask; returns popcount.
+__device__ inline int emit_mask(const ge_batch &d, int b, int lane, uint32_t *msk) {
+    int cnt = 0;
+    for (int w = lane; w < d.AW; w += 32) {
+        uint32_t m = msk[w] & tail_mask(d.A, w);
+        msk[w] = m;
+        cnt += __popc(m);
+        d.mask_bits[(size_t)b * d.AW + w] = m;
+    }
+    cnt = __reduce_add_sync(GE_FULL, cnt);
+    if (d.mask_bytes) {
+        __syncwarp();
+        uint4 *mb = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
+        for (int c = lane; c < (d.AP >> 4); c += 32) {  // 16 mask entries -> one 128-bit store
+            uint32_t bits = (msk[c >> 1] >> ((c & 1) * 16)) & 0xffffu;
+            uint4 v;
+            v.x = expand4(bits);
+            v.y = expand4(bits >> 4);
+            v.z = expand4(bits >> 8);
+            v.w = expand4(bits >> 12);
+            mb[c] = v;
+        }
+    }
+    __syncwarp();
+    return cnt;
+}
+
+// Index of edge u->v in row u (warp scan of the row), -1 if absent.  Result is warp-uniform.
+__device__ inline int find_edge(const int32_t *rp, const int32_t *col, int u, int v, int lane) {
+    int lo = rp[u], hi = rp[u + 1];
+    for (int base = lo; base < hi; base += 32) {
+        int e = base + lane;
+        bool hit = e < hi && col[e] == v;
+        unsigned bal = __ballot_sync(GE_FULL, hit);
+        if (bal) return base + __ffs(bal) - 1;
+    }
+    return -1;
+}
+
+// Source node of directed edge e (binary search over row_ptr; warp-uniform when e is).
+__device__ inline int edge_src(const int32_t *rp, int N, int e) {
+    int lo = 0, hi = N;  // invariant: rp[lo] <= e < rp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (rp[mid] <= e) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Load-balanced warp expansion of the CSR rows of a node set.
+// For every node u in `set` (NW words, in shared memory) and every edge e of row u, calls
+//     f(owner_lane, e, active)
+// from ALL 32 lanes (so f may shuffle); `owner_lane` is the lane that holds the per-node payload
+// the caller loaded in `load(u)`; `active` is false for padding lanes.  Up to 32 rows are in
+// flight at once, their edges are walked 32 per iteration in row order => coalesced segments,
+// high memory-level parallelism, no per-row serial latency chain.
+template <class Load, class Visit>
+__device__ inline void expand_set(const int32_t *rp, const uint32_t *set, int NW, int lane, Load load, Visit f) {
+    for (int w = 0; w < NW; ++w) {
+        uint32_t bits = set[w];  // warp-uniform (broadcast read)
+        if (!bits) continue;
+        int nn = __popc(bits);
+        int u = -1, lo = 0, len = 0;
+        if (lane < nn) {
+            u = (w << 5) + (int)__fns(bits, 0, lane + 1);
+            lo = rp[u];
+            len = rp[u + 1] - lo;
+        }
+        // compact away empty rows so that row starts below are distinct
+        unsigned ne = __ballot_sync(GE_FULL, len > 0);
+        int n2 = __popc(ne);
+        int from = lane < n2 ? (int)__fns(ne, 0, lane + 1) : lane;
+        u = __shfl_sync(GE_FULL, u, from);
+        lo = __shfl_sync(GE_FULL, lo, from);
+        len = __shfl_sync(GE_FULL, len, from);
+        if (lane >= n2) { u = -1; len = 0; }
+        load(u);  // caller captures payload for node u in registers of this lane
+        int pre = len;  // inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(GE_FULL, pre, o);
+            if (lane >= o) pre += t;
+        }
+        int total = __shfl_sync(GE_FULL, pre, 31);
+        pre -= len;  // exclusive
+        int base = lo - pre;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            uint32_t st = (len > 0 && pre >= t0 && pre < t0 + 32) ? (1u << (pre - t0)) : 0u;
+            st = __reduce_or_sync(GE_FULL, st);
+            int before = __popc(__ballot_sync(GE_FULL, len > 0 && pre < t0));
+            int owner = before + __popc(st & (0xffffffffu >> (31 - lane))) - 1;
+            int t = t0 + lane;
+            bool active = t < total;
+            int ob = __shfl_sync(GE_FULL, base, owner & 31);
+            f(owner & 31, ob + t, active);
+        }
+    }
+}
+
+// fp64 SSSP with optional cutoff, value semantics of nx _dijkstra_multisource
+// (nx:algorithms/shortest_paths/weighted.py:853-881): distances are left-fold fp64 path sums,
+// relaxations with dist+w > cutoff are skipped.  Frontier Bellman-Ford to the fixed point gives
+// the same values because fp64 add is monotone.  Result: s.q[v] = bit pattern of dist (+inf if
+// unreached).  Uses s.t0 / s.t1 as frontier / next.
+__device__ inline void sssp_warp(const ge_batch &d, int b, int lane, Scr &s, int source, double cutoff, bool use_cutoff) {
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    const double *w64 = d.w64 + (size_t)b * d.MP;
+    const u64 INF = 0x7ff0000000000000ull;
+    for (int v = lane; v < d.N; v += 32) s.q[v] = INF;
+    for (int w = lane; w < d.NW; w += 32) { s.t0[w] = 0; s.t1[w] = 0; }
+    __syncwarp();
+    if (lane == 0) { s.q[source] = 0ull; s.t0[source >> 5] = 1u << (source & 31); }
+    __syncwarp();
+    for (int round = 0; round < 4 * d.N + 4; ++round) {
+        double du = 0.0;
+        expand_set(
+            rp, s.t0, d.NW, lane, [&](int u) { du = u >= 0 ? __longlong_as_double((long long)s.q[u]) : 0.0; },
+            [&](int owner, int e, bool active) {
+                double dsrc = __shfl_sync(GE_FULL, du, owner);
+                if (active) {
+                    int v = col[e];
+                    double nd = dsrc + w64[e];
+                    if (!use_cutoff || nd <= cutoff) {
+                        u64 nb = (u64)__double_as_longlong(nd);
+                        u64 old = atomicMin(&s.q[v], nb);
+                        if (nb < old) atomicOr(&s.t1[v >> 5], 1u << (v & 31));
+                    }
+                }
+            });
+        __syncwarp();
+        uint32_t any = 0;
+        for (int w = lane; w < d.NW; w += 32) { uint32_t n = s.t1[w]; s.t0[w] = n; s.t1[w] = 0; any |= n; }
+        __syncwarp();
+        if (!__any_sync(GE_FULL, any != 0)) break;
+    }
+}
+
+// Reachability over the adjacency bit-matrix inside `allowed`, seeded with the bits already in
+// `reach`.  frontier/next are NW-word temporaries.  Lane w owns word w (+32k) of every set.
+__device__ inline void bfs_bits(const uint32_t *adj, int NW, int lane, const uint32_t *allowed, uint32_t *reach,
+                                uint32_t *frontier, uint32_t *next) {
+    for (int w = lane; w < NW; w += 32) frontier[w] = reach[w];
+    __syncwarp();
+    for (;;) {
+        for (int w = lane; w < NW; w += 32) next[w] = 0;
+        for (int fw = 0; fw < NW; ++fw) {
+            uint32_t bits = frontier[fw];
+            while (bits) {
+                int v = (fw << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                for (int w = lane; w < NW; w += 32) next[w] |= __ldg(&adj[(size_t)v * NW + w]);
+            }
+        }
+        __syncwarp();
+        uint32_t any = 0;
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t n = next[w] & allowed[w] & ~reach[w];
+            reach[w] |= n;
+            frontier[w] = n;
+            any |= n;
+        }
+        __syncwarp();
+        if (!__any_sync(GE_FULL, any != 0)) break;
+    }
+}
+
+}  // namespace ge

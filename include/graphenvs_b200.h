@@ -1,0 +1,167 @@
+/* graphenvs_b200.h -- C ABI of the B200-native batched GraphEnvs engine.
+ *
+ * One `ge_batch` describes B independent environment instances of ONE env kind with uniform
+ * (N nodes, M = 2*n_edges directed edges).  Every pointer in it is a DEVICE pointer owned by the
+ * caller (the Python host allocates them as torch tensors, a C host with cudaMalloc); the
+ * library allocates nothing and keeps no state between calls, so a descriptor can be copied,
+ * sliced per rank, or rebuilt freely.  All calls enqueue work on `stream` (a cudaStream_t passed
+ * as void*), return 0 on success / a negative ge_status on error (text via ge_last_error()),
+ * never throw, and are not thread-safe per descriptor.  No torch types appear here.
+ *
+ * What each entry point replaces in the reference (paths relative to graph_envs/):
+ *   ge_reset          tail of every Env.reset(): state init + first info['mask']
+ *                     (shortest_path.py:74-98, longest_path.py:82-122, steiner_tree.py:89-112,
+ *                      tsp.py:119-162, max_independent_set.py:70-89, densest_subgraph.py:68-101,
+ *                      multicast_routing.py:118-152, distribution_center.py:94-127)
+ *   ge_step           Env.step() + Env._get_mask() for the 8 envs
+ *                     (shortest_path.py:105-141, longest_path.py:125-196, steiner_tree.py:116-157,
+ *                      tsp.py:174-258, max_independent_set.py:92-124, densest_subgraph.py:105-196,
+ *                      multicast_routing.py:155-266, distribution_center.py:129-174)
+ *   ge_obs_flat       utils.vectorize_graph (utils.py:87-88), layout of utils.devectorize_graph
+ *   ge_features       feature_extraction.generate_features (feature_extraction.py:6-37)
+ *   ge_prepare        reset-time derived data: eval heuristics (shortest_path.py:88-90,
+ *                     longest_path.py:103-106, steiner_tree.py:77-85), Multicast max_distance
+ *                     (multicast_routing.py:98-103), DistributionCenter in-range tables
+ *                     (distribution_center.py:25-26,113-116)
+ *   ge_generate       instance generation of reset() (shortest_path.py:54-75 and peers) --
+ *                     distribution parity only (device RNG), see DESIGN.md
+ *   ge_sample_actions README.md:54-68 "random valid action" loop (policy stand-in for benches)
+ */
+#ifndef GRAPHENVS_B200_H
+#define GRAPHENVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GE_ABI_VERSION 1
+
+typedef enum {
+    GE_SHORTEST_PATH = 0,      /* ShortestPath-v0        shortest_path.py        node actions */
+    GE_LONGEST_PATH = 1,       /* LongestPath-v0         longest_path.py         node actions */
+    GE_STEINER_TREE = 2,       /* SteinerTree-v0 / MST   steiner_tree.py         edge actions */
+    GE_TSP = 3,                /* TSP-v0                 tsp.py                  node actions */
+    GE_MAX_INDEPENDENT_SET = 4,/* MaxIndependentSet-v0   max_independent_set.py  node actions */
+    GE_DENSEST_SUBGRAPH = 5,   /* DensestSubgraph-v0     densest_subgraph.py     node actions */
+    GE_MULTICAST_ROUTING = 6,  /* MulticastRouting-v0    multicast_routing.py    edge actions */
+    GE_DISTRIBUTION_CENTER = 7 /* DistributionCenter-v0  distribution_center.py  node actions */
+} ge_kind;
+
+typedef enum {
+    GE_OK = 0,
+    GE_ERR_ARG = -1,      /* bad descriptor / unsupported size */
+    GE_ERR_CUDA = -2,     /* CUDA runtime error, see ge_last_error() */
+    GE_ERR_UNSUPPORTED = -3
+} ge_status;
+
+/* ge_batch.flags */
+#define GE_FLAG_AUTO_RESET 1u   /* on done: re-init the env's state on its own graph inside ge_step */
+#define GE_FLAG_WEIGHTED_PR 2u  /* pagerank uses edge weights (TSP stores them as 'weight', tsp.py:90) */
+
+/* per-env status written by ge_step into flags[b].status */
+#define GE_STEP_OK 0
+#define GE_STEP_INVALID 1     /* the reference would raise AssertionError; state unchanged */
+#define GE_STEP_AFTER_DONE 2  /* env already done and auto-reset off; state unchanged */
+
+/* One 4-byte record per env per step (written with a single 32-bit store). */
+typedef struct {
+    uint8_t done;     /* 1 if this step ended the episode */
+    int8_t solved;    /* -1 = key absent from info, 0 / 1 = info['solved'] */
+    uint8_t status;   /* GE_STEP_* */
+    uint8_t has_mask; /* 0 only for LongestPath's invalid-move early return (longest_path.py:169-173) */
+} ge_step_flags;
+
+typedef struct ge_batch {
+    /* ---- shape / parameters ---- */
+    int32_t kind, B, N, M;        /* M = 2 * n_edges directed edges */
+    int32_t parenting;            /* per-env rules of SURVEY 8(b) are enforced by the host */
+    int32_t n_dests;              /* SteinerTree / MulticastRouting */
+    int32_t n_choices;            /* DensestSubgraph (already floor(N/e) when defaulted) */
+    int32_t n_targets;            /* DistributionCenter target_count (row count of in_range) */
+    uint32_t flags;
+    int32_t env_id0;              /* global id of env 0 of this slice (rank offset; feeds the action sampler) */
+    int32_t NW, MW;               /* ceil(N/32), ceil(M/32) */
+    int32_t A, AW, AP;            /* mask length (N or M), its words, byte stride (A rounded up to 16) */
+    int32_t RP, MP, ADJS;         /* strides: row_ptr (ints), col/w (elements), adj_bits (words) per env */
+    double max_distance;          /* DistributionCenter cutoff */
+
+    /* ---- graph store (static per instance) ---- */
+    const int32_t *row_ptr;       /* [B, RP]   CSR offsets, reference edge order (source-sorted) */
+    const int32_t *col;           /* [B, MP]   destination of every directed edge */
+    const float *w32;             /* [B, MP]   edge feature column 0 (float32), kinds stepping in fp32 */
+    const double *w64;            /* [B, MP]   float64 edge attribute, kinds stepping in fp64 / prepare */
+    uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived) */
+
+    /* ---- instance parameters (static) ---- */
+    int32_t *src, *dest;          /* [B] */
+    uint32_t *target_bits;        /* [B, NW]  IS_TARGET column as a bitset */
+    float *node_cost;             /* [B, N]   MIS weight / DistCenter cost column */
+    float *node_xy;               /* [B, N, 2] TSP spatial coordinates or NULL */
+    float *max_dist32;            /* [B]      Multicast MAX_DISTANCE column value */
+    int32_t *targets;             /* [B, n_targets] DistributionCenter target node ids */
+    uint32_t *in_range;           /* [B, n_targets, NW] nodes within max_distance of each target */
+    double *heuristic;            /* [B]      info['heuristic_solution'] */
+    float *features;              /* [B, N, 5] structural features or NULL (zeros in obs) */
+
+    /* ---- dynamic state ---- */
+    int32_t *head;                /* [B] */
+    uint32_t *node_bits;          /* [B, NW]  HAS_MSG / TAKEN column as a bitset */
+    uint32_t *node_bits2;         /* [B, NW]  DistCenter IS_COVERED; Densest neighbour-union */
+    uint32_t *edge_bits;          /* [B, MW]  Multicast EDGE_IS_TAKEN */
+    float *dist32;                /* [B, N]   Multicast DISTANCE_FROM_SOURCE column */
+    double *cost;                 /* [B]      running solution_cost (fp32 kinds keep a float value in it) */
+    int32_t *counters;            /* [B, 4]   k_taken, edge_cnt, constraints_satisfied, steps */
+    uint8_t *done;                /* [B] */
+    uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
+    uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
+    double *acc;                  /* [B, 4]   per-env statistics: episodes, solved, sum reward, sum final cost */
+} ge_batch;
+
+/* step outputs (device pointers) */
+typedef struct {
+    float *reward;            /* [B] */
+    ge_step_flags *flags;     /* [B] */
+    double *solution_cost;    /* [B] info['solution_cost'] (NaN = key absent) */
+} ge_step_out;
+
+int ge_abi_version(void);
+const char *ge_last_error(void);
+
+/* Fills the derived size fields (NW, MW, A, AW, AP, RP, MP, ADJS) from kind/N/M. */
+int ge_fill_layout(ge_batch *batch);
+/* Bytes of dynamic shared memory one step launch uses (for diagnostics / occupancy reports). */
+int ge_step_smem_bytes(const ge_batch *batch);
+
+int ge_build_adjacency(const ge_batch *batch, void *stream);
+/* what: bit0 heuristics (SSSP / MST where the reference's value is tie-independent),
+ *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw),
+ *       bit2 DistributionCenter in-range tables.  u01 may be NULL unless bit1 is set. */
+int ge_prepare(const ge_batch *batch, int what, const double *u01, void *stream);
+int ge_features(const ge_batch *batch, void *stream);
+int ge_generate(const ge_batch *batch, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32,
+                void *stream);
+
+/* select: device uint8[B] (1 = reset this env) or NULL for all. */
+int ge_reset(const ge_batch *batch, const uint8_t *select, void *stream);
+int ge_step(const ge_batch *batch, const int32_t *actions, const ge_step_out *out, void *stream);
+int ge_sample_actions(const ge_batch *batch, uint64_t seed, uint32_t t, int32_t *actions, void *stream);
+
+/* Reference wire format (utils.py:87-88): out is float32[count, N*F + M*Fe + 2*M]. */
+int ge_obs_len(const ge_batch *batch);
+int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *stream);
+
+/* End-to-end entry with HOST buffers: copies actions H2D, steps, copies reward / flags /
+ * solution_cost (and the byte mask when h_mask != NULL) D2H, and synchronises the stream.
+ * d_actions / out are device staging buffers owned by the caller. */
+int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
+                 float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, void *stream);
+
+/* Reduces acc[B,4] to out[4] (device double[4]): episodes, solved, sum reward, sum final cost. */
+int ge_stats(const ge_batch *batch, double *out4, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHENVS_B200_H */

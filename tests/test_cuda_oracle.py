@@ -1,0 +1,103 @@
+"""GPU: CUDA engine vs the C oracle on seeded instances (host generator = the reference's draws),
+device-sampled random valid actions, auto-reset on.  Sizes go beyond the golden fixtures
+(N > 64 exercises the multi-word bitset paths, N <= 64 the register fast paths)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import cuda_util as cu
+from graphenvs_b200 import BatchedGraphEnv
+from graphenvs_b200.instances import generate_instance
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [
+    ("ShortestPath-v0", 10, 20, {}, 24),
+    ("ShortestPath-v0", 100, 300, {}, 40),
+    ("LongestPath-v0", 50, 200, {"parenting": 2}, 60),       # BASELINE config 2 shape
+    ("LongestPath-v0", 33, 70, {"parenting": 2}, 40),
+    ("LongestPath-v0", 100, 260, {"parenting": 2}, 60),
+    ("LongestPath-v0", 90, 200, {"parenting": 3}, 60),
+    ("LongestPath-v0", 40, 100, {"parenting": 1}, 40),
+    ("SteinerTree-v0", 100, 500, {"n_dests": 99}, 120),      # config 3 shape
+    ("SteinerTree-v0", 60, 150, {"n_dests": 5}, 80),
+    ("TSP-v0", 40, 120, {"parenting": 1}, 50),
+    ("TSP-v0", 40, 120, {"parenting": 2}, 50),
+    ("TSP-v0", 70, 2415, {"parenting": 2}, 80),               # complete graph, N > 64
+    ("MaxIndependentSet-v0", 200, 600, {}, 210),
+    ("DensestSubgraph-v0", 80, 300, {"parenting": 1}, 40),
+    ("DensestSubgraph-v0", 80, 300, {"parenting": 0}, 40),
+    ("MulticastRouting-v0", 120, 600, {"parenting": 4, "n_dests": 5}, 80),
+    ("MulticastRouting-v0", 60, 200, {"parenting": 2, "n_dests": 3}, 60),
+    ("MulticastRouting-v0", 40, 120, {"parenting": 1, "n_dests": 3}, 20),
+    ("DistributionCenter-v0", 120, 500, {"parenting": 2}, 40),
+    ("DistributionCenter-v0", 90, 300, {"parenting": 1, "max_distance": 1.2}, 40),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=["%s-N%d-E%d-%s" % (c[0][:-3], c[1], c[2], "".join("%s%s" % (k[0], v) for k, v in c[3].items())) for c in CONFIGS])
+def test_random_rollout_matches_oracle(cfg):
+    env_id, N, E, kw, T = cfg
+    B, seed = 32, 7
+    env = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+    p = env.params
+    inst = []
+    for b in range(B):
+        random.seed(1000 + b)
+        np.random.seed(1000 + b)
+        inst.append(generate_instance(env_id, p))
+    u01 = None
+    if env_id == "MulticastRouting-v0":
+        u01 = torch.tensor([i.u01 for i in inst], dtype=torch.float64, device="cuda")
+    env.load_instances(inst)
+    if u01 is not None:
+        env.finalize_graphs(u01=u01)
+        md = env.t["max_dist32"].cpu().numpy()
+        for b, i in enumerate(inst):
+            i.max_distance = float(md[b])
+    oenvs = [cu.oracle_from_instance(env_id, i, p) for i in inst]
+    if env_id == "MulticastRouting-v0":  # max_distance itself: fp64 SSSP extremes, multicast_routing.py:98-103
+        for b, (i, oe) in enumerate(zip(inst, oenvs)):
+            dist = oe.sssp(0)
+            ft = max(dist[t] for t in i.dests)
+            exp = np.float32(i.u01 * (dist.max() - ft) + ft)
+            assert np.float32(md[b]) == exp
+    info = env.reset()
+    torch.cuda.synchronize()
+    masks = [oe.mask(reset_patch=True) for oe in oenvs]
+    np.testing.assert_array_equal(info["mask"].cpu().numpy(), np.stack(masks))
+    for t in range(T):
+        acts = env.sample_actions(seed, t).cpu().numpy()
+        for b in range(B):
+            assert acts[b] == orc.sample_action(masks[b], seed, b, t), "sampler parity"
+        reward, done, info = env.step(env.actions_dev)
+        torch.cuda.synchronize()
+        reward = reward.cpu().numpy(); done = done.cpu().numpy()
+        solved = info["solved"].cpu().numpy(); status = info["status"].cpu().numpy()
+        cost = info["solution_cost"].cpu().numpy(); gmask = info["mask"].cpu().numpy()
+        for b, oe in enumerate(oenvs):
+            o = oe.step(int(acts[b]))
+            tag = "%s env %d step %d" % (env_id, b, t)
+            assert status[b] == o["status"] == 0, tag
+            assert bool(done[b]) == o["done"], tag
+            assert int(solved[b]) == o["solved"], tag
+            assert abs(reward[b] - o["reward"]) <= 1e-5 * max(1.0, abs(o["reward"])), (tag, reward[b], o["reward"])
+            if np.isnan(o["solution_cost"]):
+                assert np.isnan(cost[b]), tag
+            else:
+                assert abs(cost[b] - o["solution_cost"]) <= 1e-5 * max(1.0, abs(o["solution_cost"])), tag
+            if o["done"]:
+                oe.reset_state()
+                masks[b] = oe.mask(reset_patch=True)
+            elif o["has_mask"]:
+                masks[b] = o["mask"]
+            np.testing.assert_array_equal(gmask[b], masks[b], err_msg="mask " + tag)
+    # observation wire format at the end of the rollout (features off => zeros on both sides)
+    obs = env.obs_flat().cpu().numpy()
+    for b, oe in enumerate(oenvs):
+        np.testing.assert_array_equal(obs[b], oe.obs(), err_msg="obs env %d" % b)
+    st = env.stats().cpu().numpy()
+    assert st[0] >= 1 or T < 30

@@ -1,0 +1,62 @@
+"""CPU: the seeded host-side instance generator (graphenvs_b200/instances.py) regenerates the
+reference's reset(seed) instances bit-for-bit (graph, edge order, weights, terminals, costs)."""
+import random
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from graphenvs_b200.instances import generate_instance
+from graphenvs_b200.spec import check_ctor_args
+
+CASES = list(gu.all_cases())
+
+
+@pytest.mark.parametrize("case", CASES, ids=[gu.case_id(m) for m, _ in CASES])
+def test_regenerates_reference_instance(case):
+    m, r = case
+    env_id = m["env_id"]
+    kw = dict(m["kwargs"])
+    p = check_ctor_args(env_id, kw.pop("n_nodes"), kw.pop("n_edges"), kw)
+    random.seed(m["seed"])
+    np.random.seed(m["seed"])
+    ins = generate_instance(env_id, p)
+    np.testing.assert_array_equal(ins.links, r["edge_links"])
+    if env_id not in ("MaxIndependentSet-v0", "DensestSubgraph-v0"):
+        np.testing.assert_array_equal(ins.w64, r["w64"])
+    nodes0 = r["nodes0"]
+    if env_id in ("ShortestPath-v0", "LongestPath-v0"):
+        assert (ins.src, ins.dest) == (m["src"], m["dest"])
+    elif env_id == "SteinerTree-v0":
+        assert ins.src == m["src"]
+        np.testing.assert_array_equal(ins.dests, r["dests"])
+    elif env_id == "MulticastRouting-v0":
+        np.testing.assert_array_equal(ins.dests, r["dests"])
+        assert 0.0 <= ins.u01 < 1.0
+    elif env_id == "DistributionCenter-v0":
+        np.testing.assert_array_equal(np.sort(ins.dests), r["targets"])
+        np.testing.assert_array_equal(ins.node_cost.astype(np.float32), nodes0[:, 0])
+    elif env_id == "MaxIndependentSet-v0":
+        np.testing.assert_array_equal(ins.node_cost.astype(np.float32), nodes0[:, 0])
+    elif env_id == "TSP-v0" and m["kwargs"].get("spatial"):
+        np.testing.assert_array_equal(ins.node_xy.astype(np.float32), nodes0[:, 2:4])
+    # the action stream that follows reset() must also line up: same next numpy draw
+    if m["policy"] == "random" and len(r["actions"]):
+        valid = r["mask0"].nonzero()[0]
+        assert int(np.random.choice(valid)) == int(r["actions"][0])
+
+
+def test_ctor_rules():
+    with pytest.raises(AssertionError):
+        check_ctor_args("LongestPath-v0", 10, 20, {})            # default parenting=-1 rejected
+    with pytest.raises(AssertionError):
+        check_ctor_args("TSP-v0", 10, 20, {})
+    with pytest.raises(AssertionError):
+        check_ctor_args("ShortestPath-v0", 10, 20, {"parenting": 1})
+    with pytest.raises(ValueError):
+        check_ctor_args("MulticastRouting-v0", 10, 20, {"parenting": 7})
+    with pytest.raises(TypeError):
+        check_ctor_args("MaxIndependentSet-v0", 10, 20, {"parenting": 1})
+    assert check_ctor_args("LongestPath-v0", 50, -1, {"parenting": 2})["n_edges"] == 367
+    assert check_ctor_args("DensestSubgraph-v0", 10, 20, {"parenting": 1})["n_choices"] == 3
+    assert check_ctor_args("DistributionCenter-v0", 500, 4000, {})["target_count"] == 100
