@@ -42,7 +42,7 @@ class BatchedGraphEnv:
         d.n_dests = int(P.get("n_dests", 0))
         d.n_choices = int(P.get("n_choices", 0))
         d.n_targets = int(P.get("target_count", 0))
-        d.flags = (1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0)
+        d.flags = (1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0) | (0 if P.get("weighted", True) else 4)
         d.env_id0 = int(env_id0)
         d.max_distance = float(P.get("max_distance", 0.0)) if env_id == "DistributionCenter-v0" else 0.0
         _native.check(self.lib.ge_fill_layout(C.byref(d)))

@@ -18,6 +18,15 @@ static int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+// shared with the other translation units of the library (ge_features.cu, ge_generate.cu)
+extern "C" int ge_set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 #define GE_CUDA_OK(expr)                                                                         \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \

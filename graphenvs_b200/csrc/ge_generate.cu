@@ -1,3 +1,237 @@
-// ge_generate.cu -- device-side instance generation.  Filled in below.
+// ge_generate.cu -- device-side instance generation (the graph / weight / terminal part of every
+// reference reset(), e.g. shortest_path.py:54-75).  One warp per environment; the candidate
+// graph lives as an N x NW adjacency bit-matrix in that warp's shared-memory slice.
+//
+// DISTRIBUTION parity with the reference, not stream parity: connected G(n,m) by rejection
+// (nx.gnm_random_graph: i.i.d. endpoint pairs, self-loops/duplicates rejected, until m edges;
+// whole graph rejected until connected; TSP additionally rejects degree-1 nodes and graphs whose
+// removal of node 0 disconnects them, tsp.py:60-71), weights k/10 with k~U{3..9} per undirected
+// edge, terminals uniform without replacement.  RNG is a counter-based hash, so instance b of a
+// batch is a pure function of (seed, env_id0 + b) -- rank-sliced batches equal the single-GPU batch.
+// Rows are emitted with ascending neighbour ids (the reference's insertion order is arbitrary).
+#include <cstdio>
+
 #include "ge_common.cuh"
-extern "C" int ge_generate(const ge_batch *, uint64_t, int32_t *, int32_t *, double *, float *, void *) { return GE_ERR_UNSUPPORTED; }
+
+using namespace ge;
+
+extern "C" int ge_set_error(int code, const char *fmt, ...);
+
+namespace {
+
+__device__ inline uint64_t mix64(uint64_t seed, uint64_t a, uint64_t b) {
+    uint64_t z = seed ^ (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ inline uint32_t bounded(uint32_t r, uint32_t n) { return (uint32_t)(((uint64_t)r * n) >> 32); }
+
+// reachability inside `allowed` over a shared-memory bit-matrix
+__device__ inline int reach_count(const uint32_t *mat, int NW, int lane, const uint32_t *allowed, uint32_t *reach,
+                                  uint32_t *frontier, uint32_t *next, int seed_node) {
+    for (int w = lane; w < NW; w += 32) { reach[w] = 0; frontier[w] = 0; }
+    __syncwarp();
+    if (lane == 0) { reach[seed_node >> 5] = 1u << (seed_node & 31); frontier[seed_node >> 5] = 1u << (seed_node & 31); }
+    __syncwarp();
+    for (;;) {
+        for (int w = lane; w < NW; w += 32) next[w] = 0;
+        for (int fw = 0; fw < NW; ++fw) {
+            uint32_t bits = frontier[fw];
+            while (bits) {
+                int v = (fw << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                for (int w = lane; w < NW; w += 32) next[w] |= mat[(size_t)v * NW + w];
+            }
+        }
+        __syncwarp();
+        uint32_t any = 0;
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t n = next[w] & allowed[w] & ~reach[w];
+            reach[w] |= n;
+            frontier[w] = n;
+            any |= n;
+        }
+        __syncwarp();
+        if (!__any_sync(GE_FULL, any != 0)) break;
+    }
+    int c = 0;
+    for (int w = lane; w < NW; w += 32) c += __popc(reach[w]);
+    return __reduce_add_sync(GE_FULL, c);
+}
+
+__global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col,
+                                double *__restrict__ w64, float *__restrict__ w32, int words_per_warp, int wpb, int weighted) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * wpb + warp;
+    if (b >= d.B) return;
+    const int N = d.N, NW = d.NW, E = d.M / 2;
+    const int n = (d.kind == GE_DENSEST_SUBGRAPH) ? N - 1 : N;  // densest_subgraph.py:59-65: node N-1 isolated
+    uint32_t *mat = smem + (size_t)warp * words_per_warp;
+    uint32_t *allowed = mat + (size_t)N * NW, *reach = allowed + NW, *frontier = reach + NW, *next = frontier + NW;
+    const uint64_t gid = (uint64_t)(uint32_t)(d.env_id0 + b);
+    const long long max_edges = (long long)n * (n - 1) / 2;
+
+    for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
+        for (int i = lane; i < N * NW; i += 32) mat[i] = 0;
+        __syncwarp();
+        if (E >= max_edges) {  // complete_graph, no randomness (nx:generators/random_graphs.py:294-296)
+            for (int u = lane; u < n; u += 32)
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t m = tail_mask(n, w);
+                    if (w == (u >> 5)) m &= ~(1u << (u & 31));
+                    mat[(size_t)u * NW + w] = m;
+                }
+        } else {
+            int count = 0;
+            for (uint32_t it = 0; count < E; ++it) {
+                int need = min(32, E - count);
+                bool isnew = false;
+                if (lane < need) {
+                    uint64_t r = mix64(seed, gid, ((uint64_t)attempt << 40) | ((uint64_t)it << 5) | (uint64_t)lane);
+                    int u = (int)bounded((uint32_t)r, (uint32_t)n), v = (int)bounded((uint32_t)(r >> 32), (uint32_t)n);
+                    if (u != v) {
+                        int a = min(u, v), c = max(u, v);
+                        uint32_t bit = 1u << (c & 31);
+                        uint32_t old = atomicOr(&mat[(size_t)a * NW + (c >> 5)], bit);
+                        if (!(old & bit)) {
+                            isnew = true;
+                            atomicOr(&mat[(size_t)c * NW + (a >> 5)], 1u << (a & 31));
+                        }
+                    }
+                }
+                count += __popc(__ballot_sync(GE_FULL, isnew));
+            }
+        }
+        __syncwarp();
+        for (int w = lane; w < NW; w += 32) allowed[w] = tail_mask(n, w);
+        __syncwarp();
+        if (reach_count(mat, NW, lane, allowed, reach, frontier, next, 0) != n) continue;
+        if (d.kind == GE_TSP) {
+            int bad = 0;
+            for (int u = lane; u < n; u += 32) {
+                int deg = 0;
+                for (int w = 0; w < NW; ++w) deg += __popc(mat[(size_t)u * NW + w]);
+                bad |= (deg == 1);
+            }
+            if (__any_sync(GE_FULL, bad)) continue;
+            if (lane == 0) allowed[0] &= ~1u;
+            __syncwarp();
+            if (n > 1 && reach_count(mat, NW, lane, allowed, reach, frontier, next, 1) != n - 1) continue;
+        }
+        break;
+    }
+
+    // ---- CSR (ascending neighbour ids) + weights
+    int32_t *rp = row_ptr + (size_t)b * d.RP;
+    int32_t *cl = col + (size_t)b * d.MP;
+    double *wd = w64 ? w64 + (size_t)b * d.MP : nullptr;
+    float *wf = w32 ? w32 + (size_t)b * d.MP : nullptr;
+    int running = 0;
+    if (lane == 0) rp[0] = 0;
+    for (int base = 0; base < N; base += 32) {
+        int u = base + lane, deg = 0;
+        if (u < N)
+            for (int w = 0; w < NW; ++w) deg += __popc(mat[(size_t)u * NW + w]);
+        int inc = deg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int x = __shfl_up_sync(GE_FULL, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (u < N) {
+            rp[u + 1] = running + inc;
+            int e = running + inc - deg;
+            for (int w = 0; w < NW; ++w) {
+                uint32_t bits = mat[(size_t)u * NW + w];
+                while (bits) {
+                    int v = (w << 5) + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    cl[e] = v;
+                    double wt = 1.0;
+                    if (weighted && d.kind != GE_MAX_INDEPENDENT_SET && d.kind != GE_DENSEST_SUBGRAPH) {
+                        uint64_t r = mix64(seed ^ 0x5851F42D4C957F2Dull, gid, ((uint64_t)min(u, v) << 32) | (uint64_t)max(u, v));
+                        wt = (double)(3 + (int)bounded((uint32_t)(r >> 32), 7u)) / 10.0;  // randint(3,10)/10.0
+                    }
+                    if (wd) wd[e] = wt;
+                    if (wf) wf[e] = (float)wt;
+                    ++e;
+                }
+            }
+        }
+        running += __shfl_sync(GE_FULL, inc, 31);
+    }
+    for (int e = d.M + lane; e < d.MP; e += 32) { cl[e] = 0; if (wd) wd[e] = 0; if (wf) wf[e] = 0; }
+
+    // ---- terminals / node parameters
+    const uint64_t tseed = seed ^ 0xD6E8FEB86659FD93ull;
+    if (d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH) {
+        if (lane == 0) {
+            uint64_t r = mix64(tseed, gid, 1);
+            int s = (int)bounded((uint32_t)r, (uint32_t)N), t = (int)bounded((uint32_t)(r >> 32), (uint32_t)(N - 1));
+            if (t >= s) t++;
+            d.src[b] = s;
+            d.dest[b] = t;
+        }
+    } else if (d.kind == GE_STEINER_TREE || d.kind == GE_MULTICAST_ROUTING || d.kind == GE_DISTRIBUTION_CENTER) {
+        uint32_t *tb = d.target_bits + (size_t)b * NW;
+        for (int w = lane; w < NW; w += 32) reach[w] = 0;  // chosen set
+        __syncwarp();
+        if (lane == 0) {
+            int src = 0, lo = 0;
+            if (d.kind == GE_STEINER_TREE) { src = (int)bounded((uint32_t)mix64(tseed, gid, 2), (uint32_t)N); d.src[b] = src; reach[src >> 5] |= 1u << (src & 31); }
+            if (d.kind == GE_MULTICAST_ROUTING) { d.src[b] = 0; reach[0] |= 1u; lo = 1; }
+            int want = d.kind == GE_DISTRIBUTION_CENTER ? d.n_targets : d.n_dests;
+            int avail = (d.kind == GE_DISTRIBUTION_CENTER) ? N : N - 1;
+            if (want > avail) want = avail;
+            int got = 0;
+            for (uint64_t ctr = 16; got < want; ++ctr) {
+                int v = lo + (int)bounded((uint32_t)mix64(tseed, gid, ctr), (uint32_t)(N - lo));
+                if ((reach[v >> 5] >> (v & 31)) & 1u) continue;
+                reach[v >> 5] |= 1u << (v & 31);
+                if (d.kind == GE_DISTRIBUTION_CENTER) d.targets[(size_t)b * d.n_targets + got] = v;
+                ++got;
+            }
+            if (d.kind == GE_STEINER_TREE) reach[src >> 5] &= ~(1u << (src & 31));
+            if (d.kind == GE_MULTICAST_ROUTING) reach[0] &= ~1u;
+        }
+        __syncwarp();
+        for (int w = lane; w < NW; w += 32) tb[w] = reach[w];
+    }
+    if (d.node_cost) {
+        for (int v = lane; v < N; v += 32) {
+            uint32_t r = (uint32_t)(mix64(tseed, gid, 0x100000000ull + (uint64_t)v) >> 32);
+            float c;
+            if (d.kind == GE_DISTRIBUTION_CENTER) c = (float)(1 + (int)bounded(r, 3u));          // randint(1,4)
+            else c = weighted ? (float)((double)(3 + (int)bounded(r, 7u)) / 10.0) : 1.0f;       // randint(3,10)/10
+            d.node_cost[(size_t)b * N + v] = c;
+        }
+    }
+    if (d.node_xy)
+        for (int i = lane; i < 2 * N; i += 32) d.node_xy[(size_t)b * N * 2 + i] = 0.f;
+}
+
+}  // namespace
+
+extern "C" int ge_generate(const ge_batch *d, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32, void *stream) {
+    if (!d || !row_ptr || !col) return ge_set_error(GE_ERR_ARG, "ge_generate: null buffers");
+    if (d->N > 1024) return ge_set_error(GE_ERR_UNSUPPORTED, "ge_generate: N=%d > 1024 (bit-matrix must fit one warp's shared-memory slice)", d->N);
+    const int E = d->M / 2;
+    const int n = d->kind == GE_DENSEST_SUBGRAPH ? d->N - 1 : d->N;
+    if (E < n - 1) return ge_set_error(GE_ERR_ARG, "ge_generate: n_edges=%d < n-1, graph cannot be connected", E);
+    int wpw = (d->N * d->NW + 4 * d->NW + 3) & ~3;
+    size_t per_warp = (size_t)wpw * sizeof(uint32_t);
+    int wpb = (int)((200 * 1024) / per_warp);
+    if (wpb < 1) return ge_set_error(GE_ERR_UNSUPPORTED, "ge_generate: graph too large");
+    if (wpb > GE_WPB) wpb = GE_WPB;
+    size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    int weighted = (d->flags & GE_FLAG_UNWEIGHTED) ? 0 : 1;
+    generate_kernel<<<(d->B + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(*d, seed, row_ptr, col, w64, w32, wpw, wpb, weighted);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "generate_kernel launch: %s", cudaGetErrorString(e));
+}

@@ -59,6 +59,7 @@ typedef enum {
 /* ge_batch.flags */
 #define GE_FLAG_AUTO_RESET 1u   /* on done: re-init the env's state on its own graph inside ge_step */
 #define GE_FLAG_WEIGHTED_PR 2u  /* pagerank uses edge weights (TSP stores them as 'weight', tsp.py:90) */
+#define GE_FLAG_UNWEIGHTED 4u   /* ge_generate: weighted=False (all edge weights / MIS costs 1.0) */
 
 /* per-env status written by ge_step into flags[b].status */
 #define GE_STEP_OK 0
