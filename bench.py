@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched GraphEnvs hot path on N B200s (one rank per GPU).
+
+One bench "step" = one pass of the hot path over one batch: sample one valid action per env from
+the current mask (README.md:54-68 loop; device counter RNG) and apply Env.step() + the new
+Env._get_mask() to all B resident envs, auto-reset on done.  Workloads are BASELINE.json's
+configs; the default is configs[1] (LongestPath-v0 N=50 E=200 parenting=2, 65,536 envs per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+`--impl reference` times the CPU implementation of the same path (the C restatement of the
+reference in oracle/, OpenMP over envs, all host threads) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# name -> (env_id, n_nodes, n_edges, kwargs, envs per GPU, survey bytes per env-step, description)
+WORKLOADS = {
+    "cfg2_longest_path": ("LongestPath-v0", 50, 200, dict(parenting=2, weighted=True), 65536, 1940,
+                          "LongestPath-v0 n_nodes=50 n_edges=200 weighted parenting=2, 65536 envs/GPU"),
+    "cfg1_shortest_path": ("ShortestPath-v0", 10, 20, dict(weighted=True), 65536, 100,
+                           "ShortestPath-v0 n_nodes=10 n_edges=20 weighted, 65536 envs/GPU"),
+    "cfg3_mst": ("SteinerTree-v0", 100, 500, dict(n_dests=99, weighted=True, is_eval_env=True), 32768, 5500,
+                 "SteinerTree-v0 (MST, n_dests=99) n_nodes=100 n_edges=500 eval, 32768 envs/GPU"),
+    "cfg4_tsp_p1": ("TSP-v0", 200, 19900, dict(parenting=1, weighted=True), 16384, 1900,
+                    "TSP-v0 n_nodes=200 complete parenting=1, 16384 envs/GPU"),
+    "cfg4_tsp_p2": ("TSP-v0", 200, 19900, dict(parenting=2, weighted=True), 16384, 162000,
+                    "TSP-v0 n_nodes=200 complete parenting=2, 16384 envs/GPU"),
+    "cfg4_mis": ("MaxIndependentSet-v0", 200, 5970, dict(weighted=True), 16384, 300,
+                 "MaxIndependentSet-v0 n_nodes=200 n_edges=5970, 16384 envs/GPU"),
+    "cfg5_multicast": ("MulticastRouting-v0", 500, 4000, dict(n_dests=3, parenting=4), 131072, 77000,
+                       "MulticastRouting-v0 n_nodes=500 n_edges=4000 parenting=4, 131072 envs/GPU"),
+    "cfg5_distcenter": ("DistributionCenter-v0", 500, 4000, dict(parenting=2, target_count=100, max_distance=1), 131072,
+                        75000, "DistributionCenter-v0 n_nodes=500 n_edges=4000 parenting=2, 131072 envs/GPU"),
+    "densest": ("DensestSubgraph-v0", 500, 4000, dict(parenting=1), 65536, 2000,
+                "DensestSubgraph-v0 n_nodes=500 n_edges=4000 parenting=1, 65536 envs/GPU"),
+}
+DEFAULT_WORKLOAD = "cfg2_longest_path"
+METRIC, UNIT = "env-steps/sec", "env-steps/s"
+SEED = 20260101
+
+
+def layout_bytes_per_step(env):
+    """Compulsory HBM bytes per env-step of THIS engine's data layout:
+    state read+write, action in, reward/flags/cost out, packed + byte mask out, statistics r/w,
+    plus the graph bytes the env's rule has to read once."""
+    d, N, M = env.desc, env.N, env.M
+    nw4 = d.NW * 4
+    fixed = 4 + 4 + 4 + 8 + 2 * (4 + 8 + 1) + 2 * 32 + 2 * 8   # action, reward, flags, sol, head/cost/done rw, acc rw, traj rw
+    mask = d.AW * 4 * 2 + (d.AP if env.t.get("mask_bytes") is not None else 0)  # old mask read, new written, bytes written
+    state = 2 * nw4
+    deg = M / max(N, 1)
+    k = env.env_id
+    if k == "ShortestPath-v0":
+        graph = nw4 + 8 + deg * 4 + 8
+    elif k == "LongestPath-v0":
+        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + 8 + deg * 4 + 8
+    elif k == "TSP-v0":
+        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + 8 + deg * 4 + 8
+    elif k == "SteinerTree-v0":
+        graph = 0.5 * (M * 4 + (N + 1) * 4) + 12 + nw4      # rows of tree nodes: on average half of the CSR
+    elif k == "MulticastRouting-v0":
+        graph = 0.5 * (M * 8 + (N + 1) * 4) + N * 4 + 12 + nw4 + 2 * d.MW * 4
+    elif k == "DistributionCenter-v0":
+        graph = M * 12 + (N + 1) * 4 + d.n_targets * (nw4 + 4) + 4 + 2 * nw4
+    elif k == "DensestSubgraph-v0":
+        graph = nw4 + 16 + 2 * nw4
+    else:  # MaxIndependentSet
+        graph = 4
+    return float(fixed + mask + state + graph)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw))}
+
+
+def host_policy(rng, mask):
+    """Uniform valid action per env from a bool[B, A] mask (the README loop's np.random.choice)."""
+    r = rng.random(mask.shape, dtype=np.float32)
+    r[~mask] = -1.0
+    return r.argmax(axis=1).astype(np.int32)
+
+
+# ------------------------------------------------------------------ CPU side (oracle port of the reference)
+def cpu_sample_envs(wl, n_envs, seed=1000):
+    """Host-generated instances (the reference's own draws, graphenvs_b200/instances.py) wrapped in oracle envs."""
+    import random
+
+    import cuda_util as cu
+    from graphenvs_b200.instances import generate_instance
+    from graphenvs_b200.spec import check_ctor_args
+    from oracle import oracle as orc
+    env_id, N, E, kw, _, _, _ = WORKLOADS[wl]
+    p = check_ctor_args(env_id, N, E, dict(kw))
+    envs = []
+    for b in range(n_envs):
+        random.seed(seed + b)
+        np.random.seed(seed + b)
+        ins = generate_instance(env_id, p)
+        if env_id == "MulticastRouting-v0":  # multicast_routing.py:98-103 with the oracle's own fp64 SSSP
+            tmp = cu.oracle_from_instance(env_id, ins, p)
+            dist = tmp.sssp(0)
+            ft = max(dist[t] for t in ins.dests)
+            ins.max_distance = float(np.float32(ins.u01 * (dist.max() - ft) + ft))
+        envs.append(cu.oracle_from_instance(env_id, ins, p))
+    return envs, orc
+
+
+def cpu_rate(wl, budget_s, n_envs=None):
+    """env-steps/s of the oracle port with all host threads; each pass = one env-step over the sample."""
+    env_id, N, E, kw, B, _, _ = WORKLOADS[wl]
+    if n_envs is None:
+        n_envs = int(min(B, max(64, 4_000_000 // (N * N + 2 * E))))
+    t_gen = time.time()
+    envs, orc = cpu_sample_envs(wl, n_envs)
+    t_gen = time.time() - t_gen
+    orc.rollout(envs, 2, SEED, t0=0)  # warm-up (page in, spawn the OpenMP team)
+    t, steps = 2, 0
+    t0 = time.perf_counter()
+    while True:
+        orc.rollout(envs, 1, SEED, t0=t)
+        t += 1
+        steps += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": n_envs * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d host-generated envs x %d passes (%.1f s; instance generation %.1f s untimed), oracle/graphenvs_oracle.c "
+                      "OpenMP over envs" % (n_envs, steps, dt, t_gen)}
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the CPU port; other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    wl = args.workload
+    env_id, N, E, kw, B, _, desc = WORKLOADS[wl]
+    n_envs = int(min(B, max(64, 4_000_000 // (N * N + 2 * E))))
+    envs, orc = cpu_sample_envs(wl, n_envs)
+    t = 0
+    for _ in range(max(args.warmup, 1)):
+        orc.rollout(envs, 1, SEED, t0=t)
+        t += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.rollout(envs, 1, SEED, t0=t)
+        t += 1
+    dt = time.perf_counter() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    val = n_envs * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64/f32 + bitsets", "data": "synthetic",
+            "config": {"workload": desc, "name": wl, "envs_per_step": n_envs,
+                       "note": "CPU port of the reference path (pure-Python reference cannot travel to the GPU box); "
+                               "each step = one env-step over a bounded sample of the workload"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d host-generated envs x %d passes, OpenMP over envs" % (n_envs, args.steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU side
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from graphenvs_b200 import BatchedGraphEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    env_id, N, E, kw, B, survey_bytes, desc = WORKLOADS[wl]
+    if args.envs:
+        B = args.envs
+    K, W = args.steps, args.warmup
+
+    env = BatchedGraphEnv(env_id, B, N, E, device=dev, auto_reset=True, env_id0=rank * B, **kw)
+    env.generate(seed=SEED)                       # device generator: same distribution as the reference's reset()
+    env.release_w64()
+    env.reset()
+    torch.cuda.synchronize()
+    lib_bytes = layout_bytes_per_step(env)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    st = torch.cuda.current_stream(dev)
+
+    def one_step(t, ev=None):
+        flush.fill_(t & 0xff)
+        if ev:
+            ev[0].record(st)
+        env.sample_actions(SEED, t)
+        if ev:
+            ev[1].record(st)
+        env.step_async(env.actions_dev)
+        if ev:
+            ev[2].record(st)
+
+    t = 0
+    for _ in range(W):
+        one_step(t)
+        t += 1
+    torch.cuda.synchronize()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.time()
+    for k in range(K):
+        one_step(t, events[k])
+        t += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in events])
+    kern_ms = np.array([e[1].elapsed_time(e[2]) for e in events])
+    total_ms = float(step_ms.sum())
+    tt = torch.tensor([total_ms, float(kern_ms.mean())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max, kern_ms_mean = float(tt[0]), float(tt[1])
+    value = world * B * K / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (ge_step_host), host policy between calls untimed
+    d = env.desc
+    use_bytes = d.A <= 512
+    h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_rew = torch.zeros(B, dtype=torch.float32).pin_memory()
+    h_flg = torch.zeros((B, 4), dtype=torch.uint8).pin_memory()
+    h_cost = torch.zeros(B, dtype=torch.float64).pin_memory()
+    h_mask = torch.zeros((B, d.AP), dtype=torch.uint8).pin_memory() if use_bytes else None
+    h_bits = None if use_bytes else torch.zeros((B, d.AW), dtype=torch.int32).pin_memory()
+    rng = np.random.default_rng(SEED + rank)
+
+    def host_mask():
+        if use_bytes:
+            return h_mask.numpy()[:, :d.A].astype(bool)
+        return np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
+
+    if use_bytes:
+        h_mask.copy_(env.t["mask_bytes"])
+    else:
+        h_bits.copy_(env.t["mask_bits"])
+    torch.cuda.synchronize()
+    Ke = max(3, min(K, args.e2e_steps))
+    e2e_s = 0.0
+    for k in range(3 + Ke):
+        h_act.numpy()[:] = host_policy(rng, host_mask())
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        env.step_host(h_act, h_rew, h_flg, h_cost, h_mask, h_bits)
+        c1 = time.perf_counter()
+        if k >= 3:
+            e2e_s += c1 - c0
+        assert int(h_flg.numpy()[:, 2].max()) == 0, "host policy produced an invalid action"
+    et = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * Ke / float(et[0])
+    h2d = B * 4
+    d2h = B * (4 + 4 + 8) + (B * d.AP if use_bytes else B * d.AW * 4)
+
+    # ---- episode statistics: the one collective of the path (NCCL all-reduce of 4 doubles)
+    from graphenvs_b200.sharding import reduce_stats
+    stats = reduce_stats(env.stats().clone()).cpu().numpy()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = lib_bytes * B / (kern_ms_mean * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64/f32 + bitsets", "data": "synthetic",
+            "config": {"workload": desc, "name": wl, "envs_per_gpu": B, "envs_total": B * world,
+                       "instances": "device generator ge_generate (connected G(n,m), reference weight law), seed %d" % SEED,
+                       "policy": "uniform valid action, device counter RNG (ge_sample_actions), inside the timed step",
+                       "auto_reset": True, "l2": "256 MiB flush write between timed steps (per-step CUDA events exclude it)",
+                       "byte_mask": True},
+            "clocks": clocks,
+            "gpu_launches": 2 * K,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "timed": "sum of ge_step_host calls (pinned H2D actions, step kernel, D2H reward/flags/cost/mask, sync); "
+                             "host policy between calls untimed"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "step_kernel", "kernel_ms": kern_ms_mean,
+                         "bytes_per_env_step": lib_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "survey_bytes_per_env_step": survey_bytes,
+                         "frac_survey_bytes": survey_bytes * B / (kern_ms_mean * 1e-3) / 1e9 / peak},
+            "wall_ms_per_step_incl_flush": 1e3 * (w1 - w0) / K,
+            "episodes": float(stats[0]), "solved": float(stats[1]),
+            "memory_gb_per_gpu": env.memory_bytes() / 1e9,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_rate(wl, args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and world == 1:  # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517"] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,7 @@ class GeBatch(C.Structure):
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
         ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P),
-        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("acc", _P),
+        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("acc", _P), ("traj", _P),
     ]
 
 
@@ -106,7 +106,7 @@ def lib():
     L.ge_sample_actions.argtypes = [BP, C.c_uint64, C.c_uint32, _P, _P]
     L.ge_obs_len.argtypes = [BP]
     L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
-    L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P]
+    L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]
     L.ge_stats.argtypes = [BP, _P, _P]
     if L.ge_abi_version() != 1:
         raise NativeError("ABI version mismatch")

@@ -92,6 +92,7 @@ class BatchedGraphEnv:
         if byte_mask:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
         T["acc"] = z((B, 4), torch.float64)
+        T["traj"] = z((B,), torch.int64)
         # step outputs
         self.reward = z((B,), torch.float32)
         self.flags = z((B, 4), torch.uint8)
@@ -106,7 +107,7 @@ class BatchedGraphEnv:
     def _sync_desc(self):
         for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
-                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc"):
+                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
 
@@ -195,7 +196,10 @@ class BatchedGraphEnv:
             self._features_loaded = True
         else:
             self._features_loaded = False
-        self.finalize_graphs(prepare=prepare, heuristics=self.is_eval_env and not have_heur)
+        u01 = None
+        if self.env_id == "MulticastRouting-v0" and all(i.max_distance is None and i.u01 is not None for i in instances):
+            u01 = up(np.array([i.u01 for i in instances], dtype=np.float64))  # multicast_routing.py:103 draw
+        self.finalize_graphs(prepare=prepare, heuristics=self.is_eval_env and not have_heur, u01=u01)
 
     def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None):
         """Derived static data after the CSR arrays are in place (load_instances / generate)."""
@@ -216,6 +220,37 @@ class BatchedGraphEnv:
         if features:
             _native.check(L.ge_features(C.byref(d), self._stream()))
         self._loaded = True
+
+    def export_instances(self, env_lo=0, count=None):
+        """Host copies of `count` resident instances as `Instance`s (reference edge-order contract)."""
+        from .instances import Instance
+        count = self.B - env_lo if count is None else count
+        sl = slice(env_lo, env_lo + count)
+        T, N, M, d = self.t, self.N, self.M, self.desc
+        g = lambda k: T[k][sl].cpu().numpy() if k in T else None  # noqa: E731
+        rp, col = g("row_ptr"), g("col")
+        w = g("w64") if "w64" in T else g("w32").astype(np.float64)
+        src, dest, heur = g("src"), g("dest"), g("heuristic")
+        tb, nc, xy, md, tg = g("target_bits"), g("node_cost"), g("node_xy"), g("max_dist32"), g("targets")
+        out = []
+        for i in range(count):
+            deg = np.diff(rp[i, :N + 1])
+            links = np.stack([np.repeat(np.arange(N, dtype=np.int32), deg), col[i, :M]], axis=1).astype(np.int32)
+            ins = Instance(n_nodes=N, links=links, w64=w[i, :M].astype(np.float64), src=int(src[i]), dest=int(dest[i]),
+                           heuristic=float(heur[i]))
+            if self.env_id == "DistributionCenter-v0":
+                ins.dests = tg[i, :d.n_targets].astype(np.int32)
+            elif tb is not None:
+                bits = np.unpackbits(tb[i].view(np.uint8), bitorder="little")[:N]
+                ins.dests = np.flatnonzero(bits).astype(np.int32)
+            if nc is not None:
+                ins.node_cost = nc[i].astype(np.float64)
+            if xy is not None:
+                ins.node_xy = xy[i].astype(np.float64)
+            if md is not None:
+                ins.max_distance = float(md[i])
+            out.append(ins)
+        return out
 
     def generate(self, seed=0):
         """Device-side instance generation (distribution parity with the reference's reset())."""
@@ -264,11 +299,11 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_sample_actions(C.byref(self.desc), int(seed), int(t), _ptr(out), self._stream()))
         return out
 
-    def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None):
+    def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None):
         """End-to-end C-ABI call with HOST (pinned) buffers: H2D actions, step, D2H results, sync."""
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev),
                                             C.byref(self._out), _ptr(h_reward), _ptr(h_flags), _ptr(h_cost),
-                                            _ptr(h_mask), self._stream()))
+                                            _ptr(h_mask), _ptr(h_mask_bits), self._stream()))
 
     def info(self, step=False):
         d = {"mask": self.mask, "mask_bits": self.t["mask_bits"], "heuristic_solution": self.t["heuristic"]}

@@ -50,11 +50,12 @@ __global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     EnvPtrs p = env_ptrs(d, b);
     StepRes r;
+    const int a = actions[b];
     if (d.done[b]) {  // only reachable with auto-reset off
         r.reward = 0.0; r.sol = __longlong_as_double(0x7ff8000000000000ll);
         r.done = 0; r.solved = -1; r.has_mask = 0; r.status = GE_STEP_AFTER_DONE;
     } else {
-        step_env(d, p, s, lane, b, actions[b], r);
+        step_env(d, p, s, lane, b, a, r);
     }
     if (lane == 0) {
         out.reward[b] = (float)r.reward;
@@ -62,6 +63,12 @@ __global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int
         f.done = (uint8_t)r.done; f.solved = (int8_t)r.solved; f.status = (uint8_t)r.status; f.has_mask = (uint8_t)r.has_mask;
         out.flags[b] = f;
         out.solution_cost[b] = r.sol;
+        if (d.traj) {
+            uint64_t cs = d.traj[b];
+            cs = ((cs << 7) | (cs >> 57)) ^ (uint64_t)(uint32_t)a ^ ((uint64_t)r.done << 40) ^ ((uint64_t)(r.solved & 3) << 44) ^
+                 ((uint64_t)r.status << 48);
+            d.traj[b] = cs;
+        }
         if (r.status == GE_STEP_OK) {
             double *acc = d.acc + (size_t)b * 4;
             acc[2] += r.reward;
@@ -491,7 +498,7 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
 }
 
 int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
-                 ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, void *stream) {
+                 ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * (size_t)d->B, cudaMemcpyHostToDevice, st));
     int rc = ge_step(d, d_actions, out, stream);
@@ -504,6 +511,8 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
         if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
         GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, (size_t)d->B * d->AP, cudaMemcpyDeviceToHost, st));
     }
+    if (h_mask_bits)
+        GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * (size_t)d->B * d->AW, cudaMemcpyDeviceToHost, st));
     GE_CUDA_OK(cudaStreamSynchronize(st));
     return GE_OK;
 }

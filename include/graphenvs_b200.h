@@ -118,6 +118,8 @@ typedef struct ge_batch {
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
     double *acc;                  /* [B, 4]   per-env statistics: episodes, solved, sum reward, sum final cost */
+    uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
+                                              same recurrence as oracle/graphenvs_oracle.c oenv_rollout */
 } ge_batch;
 
 /* step outputs (device pointers) */
@@ -154,10 +156,12 @@ int ge_obs_len(const ge_batch *batch);
 int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *stream);
 
 /* End-to-end entry with HOST buffers: copies actions H2D, steps, copies reward / flags /
- * solution_cost (and the byte mask when h_mask != NULL) D2H, and synchronises the stream.
+ * solution_cost (and the byte mask [B, AP] when h_mask != NULL, the packed mask [B, AW] when
+ * h_mask_bits != NULL) D2H, and synchronises the stream.
  * d_actions / out are device staging buffers owned by the caller. */
 int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
-                 float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, void *stream);
+                 float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
+                 uint32_t *h_mask_bits, void *stream);
 
 /* Reduces acc[B,4] to out[4] (device double[4]): episodes, solved, sum reward, sum final cost. */
 int ge_stats(const ge_batch *batch, double *out4, void *stream);

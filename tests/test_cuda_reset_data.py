@@ -1,0 +1,71 @@
+"""GPU: reset-time derived data computed by the CUDA engine against the reference's recorded
+values (tests/golden): structural features (feature_extraction.py:6-37), tie-independent eval
+heuristics (shortest_path.py:90, longest_path.py:105, steiner_tree.py:79,81), DistributionCenter
+in-range tables (distribution_center.py:113-116), Multicast max_distance (multicast_routing.py:98-103)."""
+import numpy as np
+import pytest
+import torch
+
+import cuda_util as cu
+import golden_util as gu
+from graphenvs_b200 import BatchedGraphEnv
+
+pytestmark = pytest.mark.gpu
+GROUPS = cu.grouped_cases()
+
+
+def _bare_instance(m, r):
+    ins = cu.instance_from_case(m, r)
+    ins.features = None
+    ins.heuristic = None
+    return ins
+
+
+@pytest.mark.parametrize("key", list(GROUPS), ids=["-".join(str(x) for x in k) for k in GROUPS])
+def test_features_and_heuristics(key):
+    cases = GROUPS[key]
+    m0 = cases[0][0]
+    kw = dict(m0["kwargs"])
+    n_nodes, n_edges = kw.pop("n_nodes"), kw.pop("n_edges")
+    kw["is_eval_env"] = True
+    env = BatchedGraphEnv(m0["env_id"], len(cases), n_nodes, n_edges, structural_features=True, **kw)
+    env.load_instances([_bare_instance(m, r) for m, r in cases])
+    torch.cuda.synchronize()
+    feats = env.t["features"].cpu().numpy()
+    heur = env.t["heuristic"].cpu().numpy()
+    nd = gu.DYN_COLS[m0["env_id"]]
+    for b, (m, r) in enumerate(cases):
+        ref32 = r["nodes0"][:, nd:]
+        # tolerance of the test: 1e-5 relative in fp32 (north_star); degree column exact
+        np.testing.assert_array_equal(feats[b][:, 0], ref32[:, 0])
+        np.testing.assert_allclose(feats[b], ref32, rtol=1e-5, atol=1e-8, err_msg="features env %d" % b)
+        np.testing.assert_allclose(feats[b], r["features64"].astype(np.float32), rtol=1e-5, atol=1e-8)
+        if env.spec.heuristic_on_device(env.params) and m["kwargs"].get("is_eval_env"):
+            assert heur[b] == pytest.approx(m["heuristic"], rel=1e-9), "heuristic env %d" % b
+    if m0["env_id"] == "DistributionCenter-v0" and env.desc.parenting == 2:
+        tab = env.t["in_range"].cpu().numpy().view(np.uint32)
+        for b, (m, r) in enumerate(cases):
+            bits = np.unpackbits(tab[b].view(np.uint8).reshape(tab.shape[1], -1), axis=1, bitorder="little")[:, :m["N"]]
+            # engine rows follow `targets` order = sorted target ids (golden_util) = r["in_range"] rows
+            np.testing.assert_array_equal(bits, r["in_range"], err_msg="in_range env %d" % b)
+
+
+def test_features_large_vs_oracle():
+    """N beyond the fixtures (multi-word bitsets, deeper BFS): CUDA features vs the C oracle's fp64 values."""
+    import random
+    from graphenvs_b200.instances import generate_instance
+    for env_id, N, E, kw in [("ShortestPath-v0", 150, 400, {}), ("TSP-v0", 60, 400, {"parenting": 1}),
+                             ("MaxIndependentSet-v0", 200, 5970, {}), ("DensestSubgraph-v0", 90, 300, {"parenting": 1})]:
+        B = 6
+        env = BatchedGraphEnv(env_id, B, N, E, structural_features=True, **kw)
+        inst = []
+        for b in range(B):
+            random.seed(50 + b); np.random.seed(50 + b)
+            inst.append(generate_instance(env_id, env.params))
+        env.load_instances(inst)
+        torch.cuda.synchronize()
+        feats = env.t["features"].cpu().numpy()
+        for b, ins in enumerate(inst):
+            oe = cu.oracle_from_instance(env_id, ins, env.params)
+            f = oe.features64(weighted_pr=(env_id == "TSP-v0")).astype(np.float32)
+            np.testing.assert_allclose(feats[b], f, rtol=1e-5, atol=1e-8, err_msg="%s env %d" % (env_id, b))
