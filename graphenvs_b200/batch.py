@@ -23,7 +23,7 @@ def _ptr(t):
 
 class BatchedGraphEnv:
     def __init__(self, env_id, num_envs, n_nodes, n_edges=-1, *, device=None, byte_mask=True, auto_reset=False,
-                 structural_features=False, env_id0=0, keep_w64=True, **kwargs):
+                 structural_features=False, env_id0=0, keep_w64=True, force_warp=False, **kwargs):
         self.lib = _native.lib()  # raises when the CUDA library is absent -- no fallback
         if not torch.cuda.is_available():
             raise _native.NativeError("graphenvs_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -42,7 +42,8 @@ class BatchedGraphEnv:
         d.n_dests = int(P.get("n_dests", 0))
         d.n_choices = int(P.get("n_choices", 0))
         d.n_targets = int(P.get("target_count", 0))
-        d.flags = (1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0) | (0 if P.get("weighted", True) else 4)
+        d.flags = ((1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0) | (0 if P.get("weighted", True) else 4)
+                   | (8 if force_warp else 0))
         d.env_id0 = int(env_id0)
         d.max_distance = float(P.get("max_distance", 0.0)) if env_id == "DistributionCenter-v0" else 0.0
         _native.check(self.lib.ge_fill_layout(C.byref(d)))
@@ -62,7 +63,8 @@ class BatchedGraphEnv:
         if self.spec.step_w == "f64" or (keep_w64 and self.spec.step_w == "f32"):
             T["w64"] = z((B, d.MP), torch.float64)
         if self.spec.uses_adj:
-            T["adj_bits"] = z((B, d.ADJS), torch.int32)
+            self._adj_store = z((B * d.ADJS + 4,), torch.int32)   # 16 B of slack for the block-wide bulk copy
+            T["adj_bits"] = self._adj_store[:B * d.ADJS].view(B, d.ADJS)
         T["src"] = z((B,), torch.int32)
         T["dest"] = z((B,), torch.int32)
         if self.spec.has_targets:
@@ -91,7 +93,7 @@ class BatchedGraphEnv:
         T["mask_bits"] = z((B, d.AW), torch.int32)
         if byte_mask:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
-        T["acc"] = z((B, 4), torch.float64)
+        T["acc"] = z((4, B), torch.float64)                      # component-major: one stream per statistic
         T["traj"] = z((B,), torch.int64)
         # step outputs
         self.reward = z((B,), torch.float32)
@@ -229,7 +231,7 @@ class BatchedGraphEnv:
         T, N, M, d = self.t, self.N, self.M, self.desc
         g = lambda k: T[k][sl].cpu().numpy() if k in T else None  # noqa: E731
         rp, col = g("row_ptr"), g("col")
-        w = g("w64") if "w64" in T else g("w32").astype(np.float64)
+        w = g("w64") if "w64" in T else (g("w32").astype(np.float64) if "w32" in T else np.ones((count, d.MP)))
         src, dest, heur = g("src"), g("dest"), g("heuristic")
         tb, nc, xy, md, tg = g("target_bits"), g("node_cost"), g("node_xy"), g("max_dist32"), g("targets")
         out = []

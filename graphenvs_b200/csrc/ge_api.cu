@@ -70,12 +70,11 @@ __global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int
             d.traj[b] = cs;
         }
         if (r.status == GE_STEP_OK) {
-            double *acc = d.acc + (size_t)b * 4;
-            acc[2] += r.reward;
+            d.acc[2 * (size_t)d.B + b] += r.reward;  // [4, B]: the per-step stream is one component wide
             if (r.done) {
-                acc[0] += 1.0;
-                if (r.solved == 1) acc[1] += 1.0;
-                if (r.sol == r.sol) acc[3] += r.sol;
+                d.acc[b] += 1.0;
+                if (r.solved == 1) d.acc[(size_t)d.B + b] += 1.0;
+                if (r.sol == r.sol) d.acc[3 * (size_t)d.B + b] += r.sol;
             }
         }
     }
@@ -334,7 +333,7 @@ __global__ void stats_kernel(ge_batch d, double *out4) {
     __shared__ double sh[4][32];
     double a[4] = {0, 0, 0, 0};
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < d.B; b += gridDim.x * blockDim.x)
-        for (int k = 0; k < 4; ++k) a[k] += d.acc[(size_t)b * 4 + k];
+        for (int k = 0; k < 4; ++k) a[k] += d.acc[(size_t)k * d.B + b];
     for (int k = 0; k < 4; ++k)
         for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(GE_FULL, a[k], o);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -350,6 +349,12 @@ __global__ void stats_kernel(ge_batch d, double *out4) {
 }
 
 }  // namespace
+
+// lane-per-env kernels for N <= 64 (ge_lane.cu)
+bool ge_lane_eligible(const ge_batch *d);
+int ge_lane_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, cudaStream_t st);
+int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
+int ge_lane_sample(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
 static int check_batch(const ge_batch *d) {
@@ -390,7 +395,12 @@ int ge_fill_layout(ge_batch *d) {
     d->RP = (d->N + 1 + 3) & ~3;
     d->MP = (d->M + 3) & ~3;
     if (d->MP == 0) d->MP = 4;
-    d->ADJS = (d->N * d->NW + 3) & ~3;
+    // adjacency bit-matrix stride: for N <= 64 the lane-per-env kernels read lane-private rows from a
+    // block-contiguous shared-memory copy, so the stride is chosen bank-conflict free (odd number
+    // of words for 32-bit rows, 2 x odd for 64-bit rows); larger graphs keep 16-byte alignment.
+    if (d->NW == 1) d->ADJS = d->N | 1;
+    else if (d->NW == 2) d->ADJS = 2 * (d->N | 1);
+    else d->ADJS = (d->N * d->NW + 3) & ~3;
     return GE_OK;
 }
 
@@ -452,6 +462,7 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
     if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
+    if (ge_lane_eligible(d)) return ge_lane_reset(d, select, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -465,6 +476,7 @@ int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, v
     int rc = check_batch(d);
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
+    if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -477,6 +489,7 @@ int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, v
 int ge_sample_actions(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
+    if (d->AW <= 2) return ge_lane_sample(d, seed, t, actions, (cudaStream_t)stream);
     sample_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, 0, (cudaStream_t)stream>>>(*d, seed, t, actions);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;

@@ -1,0 +1,408 @@
+// ge_lane.cu -- ONE LANE PER ENVIRONMENT kernels for small graphs (N <= 64, node-action kinds).
+//
+// Why: ncu on the warp-per-env step kernel at BASELINE config 2 (LongestPath N=50, B=65536) showed
+// 817 warp-instructions per env-step at 45 % issue utilisation and 6.6 % of HBM peak
+// (profiles/r01_step_kernel_cfg2_warp_per_env.md): with a 50-node graph every scalar instruction
+// of a warp is 32-wide redundant.  Here an env's node sets are single 64-bit registers of ONE
+// thread, a warp advances 32 envs, and the only graph data a step needs -- the N x NW adjacency
+// bit-matrix -- is staged for the whole block with ONE bulk asynchronous copy (cp.async.bulk,
+// SASS UBLKCP) into shared memory while the threads load their scalar state.  Per-env stride
+// ADJS is chosen so that lane-private rows fall on distinct banks (ge_fill_layout).
+//
+// Semantics are those of ge_envs.cuh (same reference line map); tests run every N <= 64 case
+// through both paths (GE_FLAG_FORCE_WARP).
+#include "ge_common.cuh"
+
+using namespace ge;
+
+extern "C" int ge_set_error(int code, const char *fmt, ...);
+
+#define GE_LANE_T 128  // threads (= envs) per block
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+__host__ __device__ inline bool lane_kind(int kind) {
+    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_MAX_INDEPENDENT_SET ||
+           kind == GE_DENSEST_SUBGRAPH;
+}
+// kinds/modes whose mask needs reachability over the residual graph => whole bit-matrix staged
+__host__ __device__ inline bool lane_stages(const ge_batch &d) {
+    return (d.kind == GE_LONGEST_PATH || d.kind == GE_TSP) && d.parenting >= 2;
+}
+
+struct Rows {  // adjacency rows of one env: shared-memory copy (staged) or global
+    const uint32_t *p;
+    int NW;
+    __device__ __forceinline__ u64 row(int r) const {
+        if (NW == 1) return (u64)p[r];
+        uint2 t = *reinterpret_cast<const uint2 *>(p + 2 * r);
+        return (u64)t.x | ((u64)t.y << 32);
+    }
+};
+
+// Worklist reachability from `seed` inside `allowed` (seed subset of allowed); stops early once
+// everything in `allowed` is reached.
+__device__ __forceinline__ u64 reach_within(const Rows &R, u64 seed, u64 allowed) {
+    u64 reach = seed, frontier = seed;
+    while (frontier) {
+        int r = __ffsll((long long)frontier) - 1;
+        frontier &= frontier - 1;
+        u64 nx = R.row(r) & allowed & ~reach;
+        reach |= nx;
+        frontier |= nx;
+        if (reach == allowed) break;
+    }
+    return reach;
+}
+
+struct LState {
+    u64 vis, aux;
+    int head, k, ecnt;
+    double cost;
+};
+
+// ---- masks (ge_envs.cuh: mask_head_row / mask_longest_path / mask_tsp / mask_densest)
+__device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows &R, const LState &s, int dest, u64 full) {
+    const int N = d.N;
+    switch (d.kind) {
+    case GE_SHORTEST_PATH: return R.row(s.head) & ~s.vis;                    // shortest_path.py:105-109
+    case GE_LONGEST_PATH: {                                                    // longest_path.py:125-145
+        if (d.parenting == 0) return full;
+        u64 m = R.row(s.head) & ~s.vis;
+        if (d.parenting < 2) return m;
+        if ((s.vis >> dest) & 1ull) return m;                                  // dest not in alt_G (:135-136)
+        u64 allowed = ~s.vis & full;
+        u64 reach = reach_within(R, 1ull << dest, allowed);
+        m &= reach;
+        if (d.parenting == 3 && __popcll(allowed) <= N / 3) m |= allowed;     // :141-143
+        return m; }
+    case GE_TSP: {                                                             // tsp.py:174-199
+        u64 m = R.row(s.head) & ~s.vis;
+        if (__popcll(s.vis) < N - 1) m &= ~1ull;                               // :178-179
+        if (d.parenting < 2) return m;
+        u64 res = ~s.vis & full & ~1ull;                                       // alt_G = all - start - taken
+        int n_res = __popcll(res);
+        u64 cand = m;
+        while (cand) {
+            int v = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            if (v == 0) continue;
+            if (n_res - 1 == 0) break;                                         // :191-192
+            u64 g = res & ~(1ull << v);
+            u64 seed = g & (~g + 1ull);                                        // lowest node of G_copy
+            if (reach_within(R, seed, g) != g) m &= ~(1ull << v);              // :193-194
+        }
+        return m; }
+    case GE_MAX_INDEPENDENT_SET: return ~s.vis & full;                         // max_independent_set.py:92-100
+    case GE_DENSEST_SUBGRAPH:                                                  // densest_subgraph.py:105-129
+        if (s.k == 0) return full;
+        if (d.parenting == 0) return ~s.vis & full;
+        return s.aux & ~s.vis & full;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ void lane_init_state(const ge_batch &d, int b, LState &s) {
+    bool seeded = d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH;
+    int src = seeded ? d.src[b] : 0;
+    s.vis = seeded ? (1ull << src) : 0ull;
+    s.aux = 0;
+    s.head = src;
+    s.k = 0;
+    s.ecnt = 0;
+    s.cost = 0.0;
+}
+
+__device__ __forceinline__ void lane_store_state(const ge_batch &d, int b, const LState &s, u64 mask, bool counters) {
+    if (d.NW == 1) {
+        d.node_bits[b] = (uint32_t)s.vis;
+        if (d.node_bits2) d.node_bits2[b] = (uint32_t)s.aux;
+    } else {
+        reinterpret_cast<uint2 *>(d.node_bits)[b] = make_uint2((uint32_t)s.vis, (uint32_t)(s.vis >> 32));
+        if (d.node_bits2) reinterpret_cast<uint2 *>(d.node_bits2)[b] = make_uint2((uint32_t)s.aux, (uint32_t)(s.aux >> 32));
+    }
+    d.head[b] = s.head;
+    d.cost[b] = s.cost;
+    if (counters) *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = make_int4(s.k, s.ecnt, 0, 0);
+    // mask: packed words + bytes (AP <= 64: up to four 128-bit stores)
+    if (d.AW == 1) d.mask_bits[b] = (uint32_t)mask;
+    else reinterpret_cast<uint2 *>(d.mask_bits)[b] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+    if (d.mask_bytes) {
+        uint4 *mb = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
+        for (int c = 0; c < (d.AP >> 4); ++c) {
+            uint32_t bits = (uint32_t)(mask >> (16 * c)) & 0xffffu;
+            mb[c] = make_uint4(expand4(bits), expand4(bits >> 4), expand4(bits >> 8), expand4(bits >> 12));
+        }
+    }
+}
+
+__device__ __forceinline__ double lane_edge_weight(const ge_batch &d, int b, int u, int v) {  // adj[u, v]; 0 when absent
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    int lo = rp[u], hi = rp[u + 1];
+    for (int e = lo; e < hi; ++e)
+        if (col[e] == v) return d.w64[(size_t)b * d.MP + e];
+    return 0.0;
+}
+
+__device__ __forceinline__ u64 load_bits64(const uint32_t *base, int b, int NW) {
+    if (NW == 1) return (u64)base[b];
+    uint2 t = reinterpret_cast<const uint2 *>(base)[b];
+    return (u64)t.x | ((u64)t.y << 32);
+}
+
+// Stages the adjacency bit-matrices of the block's envs with one bulk copy; returns this env's rows.
+__device__ __forceinline__ Rows stage_rows(const ge_batch &d, int b0, uint32_t *smem, uint64_t *bar, bool stage) {
+    Rows R;
+    R.NW = d.NW;
+    const int b = b0 + threadIdx.x;
+    if (!stage) {
+        R.p = d.adj_bits + (size_t)min(b, d.B - 1) * d.ADJS;
+        return R;
+    }
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nenv = min(GE_LANE_T, d.B - b0);
+        uint32_t bytes = ((uint32_t)nenv * (uint32_t)d.ADJS * 4u + 15u) & ~15u;  // adj_bits carries 16 B of slack
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem, d.adj_bits + (size_t)b0 * d.ADJS, bytes, bar);
+    }
+    R.p = smem + (size_t)threadIdx.x * d.ADJS;
+    return R;
+}
+
+__global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const int32_t *__restrict__ actions, ge_step_out out) {
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
+    const bool stage = lane_stages(d);
+    Rows R = stage_rows(d, b0, smem, &bar, stage);
+    const bool live = b < d.B;
+    const int N = d.N, kind = d.kind;
+    const u64 full = N == 64 ? ~0ull : ((1ull << N) - 1ull);
+    // scalar state (coalesced SoA streams) while the bulk copy is in flight
+    LState s;
+    int a = -1, dest = 0;
+    u64 oldmask = 0;
+    bool was_done = false;
+    if (live) {
+        a = actions[b];
+        s.vis = load_bits64(d.node_bits, b, d.NW);
+        s.aux = d.node_bits2 ? load_bits64(d.node_bits2, b, d.NW) : 0ull;
+        s.head = d.head[b];
+        s.cost = d.cost[b];
+        s.k = 0; s.ecnt = 0;
+        if (kind == GE_DENSEST_SUBGRAPH) { int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4); s.k = c.x; s.ecnt = c.y; }
+        oldmask = load_bits64(d.mask_bits, b, d.AW);
+        was_done = d.done[b] != 0;
+        if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) dest = d.dest[b];
+    }
+    if (stage) mbar_wait(&bar, 0);
+    if (!live) return;
+
+    double reward = 0.0, sol = __longlong_as_double(0x7ff8000000000000ll);
+    int done = 0, solved = -1, has_mask = 1, status = GE_STEP_OK;
+    u64 mask = oldmask;
+    bool write_state = false;
+
+    if (was_done) {
+        has_mask = 0; status = GE_STEP_AFTER_DONE;
+    } else if (kind == GE_TSP && a == 0 && s.head == 0) {                       // tsp.py:203-211
+        done = 1; reward = -(double)N; solved = 0; sol = -1.0;
+        mask = lane_mask(d, R, s, dest, full);
+        write_state = true;
+    } else if (!(a >= 0 && a < N && ((oldmask >> a) & 1ull))) {
+        status = GE_STEP_INVALID; has_mask = 0;
+    } else {
+        write_state = true;
+        const u64 abit = 1ull << a;
+        switch (kind) {
+        case GE_SHORTEST_PATH: {                                                // shortest_path.py:111-141
+            double w = lane_edge_weight(d, b, s.head, a);
+            reward = -w;
+            s.cost += w;
+            if (a == dest) { done = 1; solved = 1; }
+            s.vis |= abit; s.head = a;
+            mask = lane_mask(d, R, s, dest, full);
+            if (!done && mask == 0) { done = 1; reward = -(double)N; solved = 0; }
+            if (done) sol = s.cost;
+            break; }
+        case GE_LONGEST_PATH: {                                                 // longest_path.py:147-196
+            bool nb = (R.row(s.head) >> a) & 1ull, vis = (s.vis >> a) & 1ull;
+            if (d.parenting >= 1 && (!nb || vis)) { status = GE_STEP_INVALID; has_mask = 0; write_state = false; break; }
+            double w = nb ? lane_edge_weight(d, b, s.head, a) : 0.0;
+            reward = w;
+            s.cost -= w;
+            sol = s.cost;                                                       // every step (:163-165)
+            if (!nb || vis) { done = 1; solved = 0; reward = -2.0 * N; has_mask = 0; break; }  // :169-173
+            s.head = a; s.vis |= abit;
+            if (a == dest) { done = 1; solved = 1; }
+            mask = lane_mask(d, R, s, dest, full);
+            if (!done && mask == 0) { done = 1; reward = -2.0 * N; solved = 0; }
+            break; }
+        case GE_TSP: {                                                          // tsp.py:213-258
+            double w = lane_edge_weight(d, b, s.head, a);
+            reward = 0.0 - w;
+            s.cost += w;
+            s.vis |= abit; s.head = a;
+            if (__popcll(s.vis) == N && a == 0) { done = 1; solved = 1; }
+            mask = lane_mask(d, R, s, dest, full);
+            if (!done && mask == 0) { done = 1; reward -= 2.0 * N; solved = 0; }
+            if (done) sol = s.cost;
+            break; }
+        case GE_MAX_INDEPENDENT_SET: {                                          // max_independent_set.py:102-124
+            float w = d.node_cost[(size_t)b * N + a];
+            s.cost = (double)__fadd_rn((float)s.cost, w);
+            reward = -(double)w;
+            s.vis |= abit;
+            mask = ~s.vis & full;
+            if (mask == 0) { done = 1; solved = 1; sol = s.cost; }
+            break; }
+        case GE_DENSEST_SUBGRAPH: {                                             // densest_subgraph.py:135-196
+            solved = 1;
+            if (a == N - 1) { reward = 0.0; done = 1; sol = s.cost; break; }   // stop action (:148-154)
+            u64 row = R.row(a);
+            int ne = __popcll(row & s.vis);
+            s.aux |= row;
+            if (s.k == 0) reward = 0.0;
+            else reward = ((double)(s.ecnt + ne) / (double)(s.k + 1)) - ((double)s.ecnt / (double)s.k);
+            s.ecnt += ne; s.k += 1;
+            s.vis |= abit;
+            s.cost = (double)s.ecnt / (double)s.k;
+            mask = lane_mask(d, R, s, dest, full);
+            if (s.k == d.n_choices) { done = 1; sol = s.cost; }
+            break; }
+        }
+    }
+
+    out.reward[b] = (float)reward;
+    ge_step_flags f;
+    f.done = (uint8_t)done; f.solved = (int8_t)solved; f.status = (uint8_t)status; f.has_mask = (uint8_t)has_mask;
+    out.flags[b] = f;
+    out.solution_cost[b] = sol;
+    if (d.traj) {
+        u64 cs = d.traj[b];
+        d.traj[b] = ((cs << 7) | (cs >> 57)) ^ (u64)(uint32_t)a ^ ((u64)done << 40) ^ ((u64)(solved & 3) << 44) ^ ((u64)status << 48);
+    }
+    if (status == GE_STEP_OK) {
+        d.acc[2 * (size_t)d.B + b] += reward;
+        if (done) {
+            d.acc[b] += 1.0;
+            if (solved == 1) d.acc[(size_t)d.B + b] += 1.0;
+            if (sol == sol) d.acc[3 * (size_t)d.B + b] += sol;
+        }
+    }
+    if (done && (d.flags & GE_FLAG_AUTO_RESET)) {                               // tail of reset()
+        lane_init_state(d, b, s);
+        mask = lane_mask(d, R, s, dest, full);
+        if (kind == GE_TSP && mask == 0) mask = 1ull;                           // tsp.py:154-155
+        lane_store_state(d, b, s, mask, kind == GE_DENSEST_SUBGRAPH);
+    } else if (write_state) {
+        if (done) d.done[b] = 1;
+        lane_store_state(d, b, s, mask, kind == GE_DENSEST_SUBGRAPH);
+    }
+}
+
+__global__ void __launch_bounds__(GE_LANE_T) lane_reset_kernel(ge_batch d, const uint8_t *__restrict__ select) {
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
+    const bool stage = lane_stages(d);
+    Rows R = stage_rows(d, b0, smem, &bar, stage);
+    const bool live = b < d.B && (!select || select[b]);
+    int dest = 0;
+    if (live && (d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH)) dest = d.dest[b];
+    if (stage) mbar_wait(&bar, 0);
+    if (!live) return;
+    const u64 full = d.N == 64 ? ~0ull : ((1ull << d.N) - 1ull);
+    LState s;
+    lane_init_state(d, b, s);
+    u64 mask = lane_mask(d, R, s, dest, full);
+    if (d.kind == GE_TSP && mask == 0) mask = 1ull;
+    d.done[b] = 0;
+    *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = make_int4(0, 0, 0, 0);
+    lane_store_state(d, b, s, mask, false);
+}
+
+// Uniform choice among the valid mask bits, one lane per env (A <= 64); same draw as sample_kernel.
+__global__ void __launch_bounds__(256) lane_sample_kernel(ge_batch d, uint64_t seed, uint32_t t, int32_t *__restrict__ actions) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    u64 m = load_bits64(d.mask_bits, b, d.AW);
+    int total = __popcll(m), action = -1;
+    if (total > 0) {
+        uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t) * (uint64_t)total) >> 32);
+        uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+        int clo = __popc(lo);
+        action = (int)r < clo ? (int)__fns(lo, 0, (int)r + 1) : 32 + (int)__fns(hi, 0, (int)r - clo + 1);
+    }
+    actions[b] = action;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host launchers (called from ge_api.cu)
+bool ge_lane_eligible(const ge_batch *d) {
+    return d->N <= 64 && lane_kind(d->kind) && !(d->flags & GE_FLAG_FORCE_WARP) &&
+           (d->adj_bits != nullptr || d->kind == GE_MAX_INDEPENDENT_SET);
+}
+
+static size_t lane_smem(const ge_batch *d) { return lane_stages(*d) ? (size_t)GE_LANE_T * d->ADJS * 4 + 16 : 0; }
+
+template <class K>
+static int lane_prepare(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    return GE_OK;
+}
+
+int ge_lane_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, cudaStream_t st) {
+    size_t smem = lane_smem(d);
+    int rc = lane_prepare(lane_step_kernel, smem);
+    if (rc) return rc;
+    lane_step_kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, actions, *out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_step_kernel launch: %s", cudaGetErrorString(e));
+}
+
+int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st) {
+    size_t smem = lane_smem(d);
+    int rc = lane_prepare(lane_reset_kernel, smem);
+    if (rc) return rc;
+    lane_reset_kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, select);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_reset_kernel launch: %s", cudaGetErrorString(e));
+}
+
+int ge_lane_sample(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, cudaStream_t st) {
+    lane_sample_kernel<<<(d->B + 255) / 256, 256, 0, st>>>(*d, seed, t, actions);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_sample_kernel launch: %s", cudaGetErrorString(e));
+}

@@ -60,6 +60,7 @@ typedef enum {
 #define GE_FLAG_AUTO_RESET 1u   /* on done: re-init the env's state on its own graph inside ge_step */
 #define GE_FLAG_WEIGHTED_PR 2u  /* pagerank uses edge weights (TSP stores them as 'weight', tsp.py:90) */
 #define GE_FLAG_UNWEIGHTED 4u   /* ge_generate: weighted=False (all edge weights / MIS costs 1.0) */
+#define GE_FLAG_FORCE_WARP 8u   /* testing: use the warp-per-env kernels even where the lane-per-env ones apply */
 
 /* per-env status written by ge_step into flags[b].status */
 #define GE_STEP_OK 0
@@ -93,7 +94,7 @@ typedef struct ge_batch {
     const int32_t *col;           /* [B, MP]   destination of every directed edge */
     const float *w32;             /* [B, MP]   edge feature column 0 (float32), kinds stepping in fp32 */
     const double *w64;            /* [B, MP]   float64 edge attribute, kinds stepping in fp64 / prepare */
-    uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived) */
+    uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived); allocate 16 B of slack */
 
     /* ---- instance parameters (static) ---- */
     int32_t *src, *dest;          /* [B] */
@@ -117,7 +118,7 @@ typedef struct ge_batch {
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
-    double *acc;                  /* [B, 4]   per-env statistics: episodes, solved, sum reward, sum final cost */
+    double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
     uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
                                               same recurrence as oracle/graphenvs_oracle.c oenv_rollout */
 } ge_batch;
@@ -163,7 +164,7 @@ int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_act
                  float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
                  uint32_t *h_mask_bits, void *stream);
 
-/* Reduces acc[B,4] to out[4] (device double[4]): episodes, solved, sum reward, sum final cost. */
+/* Reduces acc[4,B] to out[4] (device double[4]): episodes, solved, sum reward, sum final cost. */
 int ge_stats(const ge_batch *batch, double *out4, void *stream);
 
 #ifdef __cplusplus

@@ -6,6 +6,9 @@ import numpy as np
 import golden_util as gu
 
 
+LANE_KINDS = ("ShortestPath-v0", "LongestPath-v0", "TSP-v0", "MaxIndependentSet-v0", "DensestSubgraph-v0")
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:12]
 

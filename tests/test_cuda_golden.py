@@ -11,10 +11,13 @@ pytestmark = pytest.mark.gpu
 GROUPS = cu.grouped_cases()
 
 
+@pytest.mark.parametrize("path", ["auto", "warp"])  # auto = lane-per-env kernels where they apply (N <= 64)
 @pytest.mark.parametrize("key", list(GROUPS), ids=["-".join(str(x) for x in k) for k in GROUPS])
-def test_replay_group(key):
+def test_replay_group(key, path):
     cases = GROUPS[key]
-    env = cu.batch_from_cases(cases)
+    if path == "warp" and not (key[1] <= 64 and key[0] in cu.LANE_KINDS):
+        pytest.skip("warp-per-env is already the auto path here")
+    env = cu.batch_from_cases(cases, force_warp=(path == "warp"))
     B = len(cases)
     info = env.reset()
     torch.cuda.synchronize()

@@ -19,6 +19,14 @@ CONFIGS = [
     ("ShortestPath-v0", 100, 300, {}, 40),
     ("LongestPath-v0", 50, 200, {"parenting": 2}, 60),       # BASELINE config 2 shape
     ("LongestPath-v0", 33, 70, {"parenting": 2}, 40),
+    ("LongestPath-v0", 64, 200, {"parenting": 2}, 60),
+    ("LongestPath-v0", 32, 80, {"parenting": 3}, 40),
+    ("LongestPath-v0", 20, 50, {"parenting": 0}, 30),
+    ("TSP-v0", 64, 300, {"parenting": 2}, 80),
+    ("TSP-v0", 24, 276, {"parenting": 2}, 40),
+    ("MaxIndependentSet-v0", 50, 200, {}, 60),
+    ("DensestSubgraph-v0", 64, 300, {"parenting": 1}, 40),
+    ("DensestSubgraph-v0", 30, 100, {"parenting": 0}, 30),
     ("LongestPath-v0", 100, 260, {"parenting": 2}, 60),
     ("LongestPath-v0", 90, 200, {"parenting": 3}, 60),
     ("LongestPath-v0", 40, 100, {"parenting": 1}, 40),
@@ -39,10 +47,13 @@ CONFIGS = [
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=["%s-N%d-E%d-%s" % (c[0][:-3], c[1], c[2], "".join("%s%s" % (k[0], v) for k, v in c[3].items())) for c in CONFIGS])
-def test_random_rollout_matches_oracle(cfg):
+@pytest.mark.parametrize("path", ["auto", "warp"])
+def test_random_rollout_matches_oracle(cfg, path):
     env_id, N, E, kw, T = cfg
-    B, seed = 32, 7
-    env = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+    if path == "warp" and not (N <= 64 and env_id in cu.LANE_KINDS):
+        pytest.skip("warp-per-env is already the auto path here")
+    B, seed = 150, 7   # not a multiple of the 128-env block of the lane kernels
+    env = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, force_warp=(path == "warp"), **kw)
     p = env.params
     inst = []
     for b in range(B):
@@ -81,7 +92,13 @@ def test_random_rollout_matches_oracle(cfg):
         for b, oe in enumerate(oenvs):
             o = oe.step(int(acts[b]))
             tag = "%s env %d step %d" % (env_id, b, t)
-            assert status[b] == o["status"] == 0, tag
+            assert status[b] == o["status"], tag
+            if o["status"] != 0:
+                # only reachable with LongestPath parenting=3, whose late-game mask re-enables non-neighbours
+                # that step() then rejects (longest_path.py:141-143 vs :153): AssertionError, state unchanged
+                assert env_id == "LongestPath-v0" and kw.get("parenting") == 3, tag
+                np.testing.assert_array_equal(gmask[b], masks[b], err_msg="mask " + tag)
+                continue
             assert bool(done[b]) == o["done"], tag
             assert int(solved[b]) == o["solved"], tag
             assert abs(reward[b] - o["reward"]) <= 1e-5 * max(1.0, abs(o["reward"])), (tag, reward[b], o["reward"])
