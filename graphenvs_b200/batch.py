@@ -65,6 +65,8 @@ class BatchedGraphEnv:
         if self.spec.uses_adj:
             self._adj_store = z((B * d.ADJS + 4,), torch.int32)   # 16 B of slack for the block-wide bulk copy
             T["adj_bits"] = self._adj_store[:B * d.ADJS].view(B, d.ADJS)
+            if N <= 64 and self.spec.step_w == "f64":
+                T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
         T["src"] = z((B,), torch.int32)
         T["dest"] = z((B,), torch.int32)
         if self.spec.has_targets:
@@ -90,15 +92,20 @@ class BatchedGraphEnv:
         T["cost"] = z((B,), torch.float64)
         T["counters"] = z((B, 4), torch.int32)
         T["done"] = z((B,), torch.uint8)
-        T["mask_bits"] = z((B, d.AW), torch.int32)
+        # step outputs + packed mask live back to back in one block => one D2H copy in ge_step_host
+        Bp = (B + 1) & ~1
+        self._io = z((16 * Bp + 4 * B * d.AW,), torch.uint8)
+        self._io_layout = (Bp, 16 * Bp + 4 * B * d.AW)
+        T["mask_bits"] = self._io[16 * Bp:].view(torch.int32).view(B, d.AW)
         if byte_mask:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
         T["acc"] = z((4, B), torch.float64)                      # component-major: one stream per statistic
         T["traj"] = z((B,), torch.int64)
+        self.step_count = None  # enable_step_counter(): device counter for CUDA-graph replays
         # step outputs
-        self.reward = z((B,), torch.float32)
-        self.flags = z((B, 4), torch.uint8)
-        self.solution_cost = z((B,), torch.float64)
+        self.reward = self._io[:4 * B].view(torch.float32)
+        self.flags = self._io[4 * Bp:4 * Bp + 4 * B].view(B, 4)
+        self.solution_cost = self._io[8 * Bp:8 * Bp + 8 * B].view(torch.float64)
         self.actions_dev = z((B,), torch.int32)
         self._stats = z((4,), torch.float64)
         self._sync_desc()
@@ -107,11 +114,19 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
+
+    def enable_step_counter(self):
+        """Device-side launch counter: ge_step increments it, ge_sample_actions adds it to `t`, so a
+        captured CUDA graph (frozen kernel arguments) draws fresh actions on every replay."""
+        if self.step_count is None:
+            self.step_count = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            self.desc.step_count = self.step_count.data_ptr()
+        return self.step_count
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -300,6 +315,14 @@ class BatchedGraphEnv:
         out = self.actions_dev if out is None else out
         _native.check(self.lib.ge_sample_actions(C.byref(self.desc), int(seed), int(t), _ptr(out), self._stream()))
         return out
+
+    def host_io(self):
+        """Pinned host mirror of the device output block: (block, reward, flags, solution_cost, mask_bits) views."""
+        Bp, nbytes = self._io_layout
+        B, AW = self.B, self.desc.AW
+        blk = torch.zeros((nbytes,), dtype=torch.uint8).pin_memory()
+        return (blk, blk[:4 * B].view(torch.float32), blk[4 * Bp:4 * Bp + 4 * B].view(B, 4),
+                blk[8 * Bp:8 * Bp + 8 * B].view(torch.float64), blk[16 * Bp:].view(torch.int32).view(B, AW))
 
     def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None):
         """End-to-end C-ABI call with HOST (pinned) buffers: H2D actions, step, D2H results, sync."""

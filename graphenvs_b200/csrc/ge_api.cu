@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
     if (b >= d.B) return;
+    if (b == 0 && lane == 0 && d.step_count) *d.step_count += 1;  // read only by later launches (sampler)
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     EnvPtrs p = env_ptrs(d, b);
     StepRes r;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) sample_kernel(ge_batch d, uint64_
     const int b = blockIdx.x * GE_WPB + warp;
     if (b >= d.B) return;
     const uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
+    if (d.step_count) t += *d.step_count;
     int total = 0;
     for (int w = lane; w < d.AW; w += 32) total += __popc(mb[w]);
     total = __reduce_add_sync(GE_FULL, total);
@@ -149,6 +151,15 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
             int c = col[e];
             atomicOr(&adj[(size_t)u * d.NW + (c >> 5)], 1u << (c & 31));
         }
+    if (d.wmat && d.w64) {  // dense float64 weights (the reference's self.adj, shortest_path.py:82)
+        double *wm = d.wmat + (size_t)b * d.N * d.N;
+        const double *w64 = d.w64 + (size_t)b * d.MP;
+        for (int i = lane; i < d.N * d.N; i += 32) wm[i] = 0.0;
+        __syncwarp();
+        __threadfence_block();
+        for (int u = lane; u < d.N; u += 32)
+            for (int e = rp[u]; e < rp[u + 1]; ++e) wm[(size_t)u * d.N + col[e]] = w64[e];
+    }
 }
 
 // Reference wire format (utils.py:87-88): [nodes.ravel | edges.ravel | edge_links.ravel] float32.
@@ -374,11 +385,26 @@ static int launch_cfg(const ge_batch *d, int jobs, int *blocks, int *wpw, size_t
     return GE_OK;
 }
 
-template <class K>
-static int set_smem(K kernel, size_t smem) {
-    if (smem > 48 * 1024) GE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// Opt-in dynamic shared memory above 48 KB, remembered per kernel so that repeated (and captured)
+// launches make no attribute call.  Shared with ge_lane.cu.
+int ge_grant_smem(const void *kernel, size_t smem) {
+    static struct { const void *k; size_t granted; } table[32];
+    static int n = 0;
+    if (smem <= 48 * 1024) return GE_OK;
+    int i = 0;
+    for (; i < n; ++i) if (table[i].k == kernel) break;
+    if (i == n) {
+        if (n == 32) return fail(GE_ERR_ARG, "kernel table full");
+        table[n].k = kernel; table[n].granted = 48 * 1024; ++n;
+    }
+    if (smem > table[i].granted) {
+        GE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        table[i].granted = smem;
+    }
     return GE_OK;
 }
+template <class K>
+static int set_smem(K kernel, size_t smem) { return ge_grant_smem((const void *)kernel, smem); }
 
 extern "C" {
 
@@ -513,19 +539,31 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
 int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                  ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * (size_t)d->B, cudaMemcpyHostToDevice, st));
+    const size_t B = (size_t)d->B;
+    GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
     int rc = ge_step(d, d_actions, out, stream);
     if (rc) return rc;
-    GE_CUDA_OK(cudaMemcpyAsync(h_reward, out->reward, sizeof(float) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
-    GE_CUDA_OK(cudaMemcpyAsync(h_flags, out->flags, sizeof(ge_step_flags) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
-    if (h_solution_cost)
-        GE_CUDA_OK(cudaMemcpyAsync(h_solution_cost, out->solution_cost, sizeof(double) * (size_t)d->B, cudaMemcpyDeviceToHost, st));
+    // When the caller laid reward | flags | solution_cost | mask_bits out back to back on BOTH sides
+    // (ge_io_bytes / BatchedGraphEnv does), the results come back with ONE copy instead of four.
+    const char *dr = (const char *)out->reward, *hr = (const char *)h_reward;
+    bool packed = h_solution_cost && h_mask_bits && (const char *)out->flags == dr + 4 * B &&
+                  (const char *)out->solution_cost == dr + 8 * B && (const char *)d->mask_bits == dr + 16 * B &&
+                  (const char *)h_flags == hr + 4 * B && (const char *)h_solution_cost == hr + 8 * B &&
+                  (const char *)h_mask_bits == hr + 16 * B;
+    if (packed) {
+        GE_CUDA_OK(cudaMemcpyAsync(h_reward, out->reward, 16 * B + sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
+    } else {
+        GE_CUDA_OK(cudaMemcpyAsync(h_reward, out->reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+        GE_CUDA_OK(cudaMemcpyAsync(h_flags, out->flags, sizeof(ge_step_flags) * B, cudaMemcpyDeviceToHost, st));
+        if (h_solution_cost)
+            GE_CUDA_OK(cudaMemcpyAsync(h_solution_cost, out->solution_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        if (h_mask_bits)
+            GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
+    }
     if (h_mask) {
         if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
-        GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, (size_t)d->B * d->AP, cudaMemcpyDeviceToHost, st));
+        GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
     }
-    if (h_mask_bits)
-        GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * (size_t)d->B * d->AW, cudaMemcpyDeviceToHost, st));
     GE_CUDA_OK(cudaStreamSynchronize(st));
     return GE_OK;
 }

@@ -202,8 +202,10 @@ __device__ inline void sssp_warp(const ge_batch &d, int b, int lane, Scr &s, int
 
 // Reachability over the adjacency bit-matrix inside `allowed`, seeded with the bits already in
 // `reach`.  frontier/next are NW-word temporaries.  Lane w owns word w (+32k) of every set.
+// With stop_at >= 0 the search ends as soon as |reach| == stop_at (connectivity tests: everything
+// allowed has been reached, expanding the last level cannot add anything).
 __device__ inline void bfs_bits(const uint32_t *adj, int NW, int lane, const uint32_t *allowed, uint32_t *reach,
-                                uint32_t *frontier, uint32_t *next) {
+                                uint32_t *frontier, uint32_t *next, int stop_at = -1) {
     for (int w = lane; w < NW; w += 32) frontier[w] = reach[w];
     __syncwarp();
     for (;;) {
@@ -218,14 +220,18 @@ __device__ inline void bfs_bits(const uint32_t *adj, int NW, int lane, const uin
         }
         __syncwarp();
         uint32_t any = 0;
+        int cnt = 0;
         for (int w = lane; w < NW; w += 32) {
             uint32_t n = next[w] & allowed[w] & ~reach[w];
-            reach[w] |= n;
+            uint32_t r = reach[w] | n;
+            reach[w] = r;
             frontier[w] = n;
             any |= n;
+            cnt += __popc(r);
         }
         __syncwarp();
         if (!__any_sync(GE_FULL, any != 0)) break;
+        if (stop_at >= 0 && __reduce_add_sync(GE_FULL, cnt) == stop_at) break;
     }
 }
 

@@ -151,7 +151,7 @@ __device__ inline void mask_tsp(const ge_batch &d, const EnvPtrs &p, Scr &s, int
             first = __reduce_min_sync(GE_FULL, first);
             if (lane == 0) s.t3[first >> 5] = 1u << (first & 31);
             __syncwarp();
-            bfs_bits(p.adj, d.NW, lane, s.t2, s.t3, s.t0, s.t1);
+            bfs_bits(p.adj, d.NW, lane, s.t2, s.t3, s.t0, s.t1, n_res - 1);
             int reached = 0;
             for (int w = lane; w < d.NW; w += 32) reached += __popc(s.t3[w]);
             reached = __reduce_add_sync(GE_FULL, reached);

@@ -54,19 +54,32 @@ __host__ __device__ inline bool lane_stages(const ge_batch &d) {
     return (d.kind == GE_LONGEST_PATH || d.kind == GE_TSP) && d.parenting >= 2;
 }
 
-struct Rows {  // adjacency rows of one env: shared-memory copy (staged) or global
+template <bool STAGED>
+struct Rows {  // adjacency rows of one env: shared-memory copy (STAGED, explicit LDS) or global
     const uint32_t *p;
+    uint32_t sp;  // shared-window address of the env's rows when STAGED
     int NW;
     __device__ __forceinline__ u64 row(int r) const {
-        if (NW == 1) return (u64)p[r];
-        uint2 t = *reinterpret_cast<const uint2 *>(p + 2 * r);
+        if (STAGED) {
+            if (NW == 1) {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sp + 4u * (uint32_t)r));
+                return (u64)v;
+            }
+            u64 v;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sp + 8u * (uint32_t)r));
+            return v;
+        }
+        if (NW == 1) return (u64)__ldg(p + r);
+        uint2 t = __ldg(reinterpret_cast<const uint2 *>(p + 2 * r));
         return (u64)t.x | ((u64)t.y << 32);
     }
 };
 
 // Worklist reachability from `seed` inside `allowed` (seed subset of allowed); stops early once
 // everything in `allowed` is reached.
-__device__ __forceinline__ u64 reach_within(const Rows &R, u64 seed, u64 allowed) {
+template <bool STAGED>
+__device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64 allowed) {
     u64 reach = seed, frontier = seed;
     while (frontier) {
         int r = __ffsll((long long)frontier) - 1;
@@ -86,7 +99,8 @@ struct LState {
 };
 
 // ---- masks (ge_envs.cuh: mask_head_row / mask_longest_path / mask_tsp / mask_densest)
-__device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows &R, const LState &s, int dest, u64 full) {
+template <bool STAGED>
+__device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows<STAGED> &R, const LState &s, int dest, u64 full) {
     const int N = d.N;
     switch (d.kind) {
     case GE_SHORTEST_PATH: return R.row(s.head) & ~s.vis;                    // shortest_path.py:105-109
@@ -126,9 +140,8 @@ __device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows &R, const
     return 0;
 }
 
-__device__ __forceinline__ void lane_init_state(const ge_batch &d, int b, LState &s) {
+__device__ __forceinline__ void lane_init_state(const ge_batch &d, int src, LState &s) {  // src = 0 for unseeded kinds
     bool seeded = d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH;
-    int src = seeded ? d.src[b] : 0;
     s.vis = seeded ? (1ull << src) : 0ull;
     s.aux = 0;
     s.head = src;
@@ -160,13 +173,10 @@ __device__ __forceinline__ void lane_store_state(const ge_batch &d, int b, const
     }
 }
 
-__device__ __forceinline__ double lane_edge_weight(const ge_batch &d, int b, int u, int v) {  // adj[u, v]; 0 when absent
-    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
-    const int32_t *col = d.col + (size_t)b * d.MP;
-    int lo = rp[u], hi = rp[u + 1];
-    for (int e = lo; e < hi; ++e)
-        if (col[e] == v) return d.w64[(size_t)b * d.MP + e];
-    return 0.0;
+// adj[u, v] of the reference's dense float64 matrix (shortest_path.py:82); 0 when there is no edge.
+// One dependent load from the resident N x N matrix instead of a CSR row scan.
+__device__ __forceinline__ double lane_edge_weight(const ge_batch &d, int b, int u, int v) {
+    return __ldg(d.wmat + ((size_t)b * d.N + u) * d.N + v);
 }
 
 __device__ __forceinline__ u64 load_bits64(const uint32_t *base, int b, int NW) {
@@ -176,11 +186,13 @@ __device__ __forceinline__ u64 load_bits64(const uint32_t *base, int b, int NW) 
 }
 
 // Stages the adjacency bit-matrices of the block's envs with one bulk copy; returns this env's rows.
-__device__ __forceinline__ Rows stage_rows(const ge_batch &d, int b0, uint32_t *smem, uint64_t *bar, bool stage) {
-    Rows R;
+template <bool STAGED>
+__device__ __forceinline__ Rows<STAGED> stage_rows(const ge_batch &d, int b0, uint32_t *smem, uint64_t *bar) {
+    Rows<STAGED> R;
     R.NW = d.NW;
+    R.sp = 0;
     const int b = b0 + threadIdx.x;
-    if (!stage) {
+    if (!STAGED) {
         R.p = d.adj_bits + (size_t)min(b, d.B - 1) * d.ADJS;
         return R;
     }
@@ -193,22 +205,25 @@ __device__ __forceinline__ Rows stage_rows(const ge_batch &d, int b0, uint32_t *
         bulk_g2s(smem, d.adj_bits + (size_t)b0 * d.ADJS, bytes, bar);
     }
     R.p = smem + (size_t)threadIdx.x * d.ADJS;
+    R.sp = smem_u32(R.p);
     return R;
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const int32_t *__restrict__ actions, ge_step_out out) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
-    const bool stage = lane_stages(d);
-    Rows R = stage_rows(d, b0, smem, &bar, stage);
+    Rows<STAGED> R = stage_rows<STAGED>(d, b0, smem, &bar);
     const bool live = b < d.B;
     const int N = d.N, kind = d.kind;
     const u64 full = N == 64 ? ~0ull : ((1ull << N) - 1ull);
     // scalar state (coalesced SoA streams) while the bulk copy is in flight
     LState s;
-    int a = -1, dest = 0;
-    u64 oldmask = 0;
+    int a = -1, dest = 0, src = 0;
+    u64 oldmask = 0, cs = 0;
+    double acc_r = 0.0, w_edge = 0.0;
+    float w_node = 0.f;
     bool was_done = false;
     if (live) {
         a = actions[b];
@@ -220,10 +235,17 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         if (kind == GE_DENSEST_SUBGRAPH) { int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4); s.k = c.x; s.ecnt = c.y; }
         oldmask = load_bits64(d.mask_bits, b, d.AW);
         was_done = d.done[b] != 0;
-        if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) dest = d.dest[b];
+        if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) { dest = d.dest[b]; src = d.src[b]; }
+        acc_r = d.acc[2 * (size_t)d.B + b];
+        if (d.traj) cs = d.traj[b];
+        // the one dependent load of the step, issued before waiting for the staged rows
+        const bool needs_w = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP;
+        if (needs_w && a >= 0 && a < N) w_edge = lane_edge_weight(d, b, s.head, a);
+        if (kind == GE_MAX_INDEPENDENT_SET && a >= 0 && a < N) w_node = d.node_cost[(size_t)b * N + a];
     }
-    if (stage) mbar_wait(&bar, 0);
+    if (STAGED) mbar_wait(&bar, 0);
     if (!live) return;
+    if (b == 0 && d.step_count) *d.step_count += 1;  // read only by later launches (sampler)
 
     double reward = 0.0, sol = __longlong_as_double(0x7ff8000000000000ll);
     int done = 0, solved = -1, has_mask = 1, status = GE_STEP_OK;
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         const u64 abit = 1ull << a;
         switch (kind) {
         case GE_SHORTEST_PATH: {                                                // shortest_path.py:111-141
-            double w = lane_edge_weight(d, b, s.head, a);
+            double w = w_edge;
             reward = -w;
             s.cost += w;
             if (a == dest) { done = 1; solved = 1; }
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         case GE_LONGEST_PATH: {                                                 // longest_path.py:147-196
             bool nb = (R.row(s.head) >> a) & 1ull, vis = (s.vis >> a) & 1ull;
             if (d.parenting >= 1 && (!nb || vis)) { status = GE_STEP_INVALID; has_mask = 0; write_state = false; break; }
-            double w = nb ? lane_edge_weight(d, b, s.head, a) : 0.0;
+            double w = nb ? w_edge : 0.0;
             reward = w;
             s.cost -= w;
             sol = s.cost;                                                       // every step (:163-165)
@@ -266,7 +288,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
             if (!done && mask == 0) { done = 1; reward = -2.0 * N; solved = 0; }
             break; }
         case GE_TSP: {                                                          // tsp.py:213-258
-            double w = lane_edge_weight(d, b, s.head, a);
+            double w = w_edge;
             reward = 0.0 - w;
             s.cost += w;
             s.vis |= abit; s.head = a;
@@ -276,7 +298,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
             if (done) sol = s.cost;
             break; }
         case GE_MAX_INDEPENDENT_SET: {                                          // max_independent_set.py:102-124
-            float w = d.node_cost[(size_t)b * N + a];
+            float w = w_node;
             s.cost = (double)__fadd_rn((float)s.cost, w);
             reward = -(double)w;
             s.vis |= abit;
@@ -305,12 +327,10 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
     f.done = (uint8_t)done; f.solved = (int8_t)solved; f.status = (uint8_t)status; f.has_mask = (uint8_t)has_mask;
     out.flags[b] = f;
     out.solution_cost[b] = sol;
-    if (d.traj) {
-        u64 cs = d.traj[b];
+    if (d.traj)
         d.traj[b] = ((cs << 7) | (cs >> 57)) ^ (u64)(uint32_t)a ^ ((u64)done << 40) ^ ((u64)(solved & 3) << 44) ^ ((u64)status << 48);
-    }
     if (status == GE_STEP_OK) {
-        d.acc[2 * (size_t)d.B + b] += reward;
+        d.acc[2 * (size_t)d.B + b] = acc_r + reward;
         if (done) {
             d.acc[b] += 1.0;
             if (solved == 1) d.acc[(size_t)d.B + b] += 1.0;
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         }
     }
     if (done && (d.flags & GE_FLAG_AUTO_RESET)) {                               // tail of reset()
-        lane_init_state(d, b, s);
+        lane_init_state(d, src, s);
         mask = lane_mask(d, R, s, dest, full);
         if (kind == GE_TSP && mask == 0) mask = 1ull;                           // tsp.py:154-155
         lane_store_state(d, b, s, mask, kind == GE_DENSEST_SUBGRAPH);
@@ -328,20 +348,20 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
     }
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(GE_LANE_T) lane_reset_kernel(ge_batch d, const uint8_t *__restrict__ select) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
-    const bool stage = lane_stages(d);
-    Rows R = stage_rows(d, b0, smem, &bar, stage);
+    Rows<STAGED> R = stage_rows<STAGED>(d, b0, smem, &bar);
     const bool live = b < d.B && (!select || select[b]);
-    int dest = 0;
-    if (live && (d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH)) dest = d.dest[b];
-    if (stage) mbar_wait(&bar, 0);
+    int dest = 0, src = 0;
+    if (live && (d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH)) { dest = d.dest[b]; src = d.src[b]; }
+    if (STAGED) mbar_wait(&bar, 0);
     if (!live) return;
     const u64 full = d.N == 64 ? ~0ull : ((1ull << d.N) - 1ull);
     LState s;
-    lane_init_state(d, b, s);
+    lane_init_state(d, src, s);
     u64 mask = lane_mask(d, R, s, dest, full);
     if (d.kind == GE_TSP && mask == 0) mask = 1ull;
     d.done[b] = 0;
@@ -354,6 +374,7 @@ __global__ void __launch_bounds__(256) lane_sample_kernel(ge_batch d, uint64_t s
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= d.B) return;
     u64 m = load_bits64(d.mask_bits, b, d.AW);
+    if (d.step_count) t += *d.step_count;
     int total = __popcll(m), action = -1;
     if (total > 0) {
         uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t) * (uint64_t)total) >> 32);
@@ -374,29 +395,28 @@ bool ge_lane_eligible(const ge_batch *d) {
 
 static size_t lane_smem(const ge_batch *d) { return lane_stages(*d) ? (size_t)GE_LANE_T * d->ADJS * 4 + 16 : 0; }
 
+int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 template <class K>
-static int lane_prepare(K kernel, size_t smem) {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-    return GE_OK;
-}
+static int lane_prepare(K kernel, size_t smem) { return ge_grant_smem((const void *)kernel, smem); }
 
 int ge_lane_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, cudaStream_t st) {
     size_t smem = lane_smem(d);
-    int rc = lane_prepare(lane_step_kernel, smem);
+    const bool needs_w = d->kind == GE_SHORTEST_PATH || d->kind == GE_LONGEST_PATH || d->kind == GE_TSP;
+    if (needs_w && !d->wmat) return ge_set_error(GE_ERR_ARG, "kind %d with N <= 64 needs wmat (ge_build_adjacency fills it)", d->kind);
+    auto kernel = lane_stages(*d) ? lane_step_kernel<true> : lane_step_kernel<false>;
+    int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
-    lane_step_kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, actions, *out);
+    kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, actions, *out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_step_kernel launch: %s", cudaGetErrorString(e));
 }
 
 int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st) {
     size_t smem = lane_smem(d);
-    int rc = lane_prepare(lane_reset_kernel, smem);
+    auto kernel = lane_stages(*d) ? lane_reset_kernel<true> : lane_reset_kernel<false>;
+    int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
-    lane_reset_kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, select);
+    kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, select);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_reset_kernel launch: %s", cudaGetErrorString(e));
 }

@@ -95,6 +95,8 @@ typedef struct ge_batch {
     const float *w32;             /* [B, MP]   edge feature column 0 (float32), kinds stepping in fp32 */
     const double *w64;            /* [B, MP]   float64 edge attribute, kinds stepping in fp64 / prepare */
     uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived); allocate 16 B of slack */
+    double *wmat;                 /* [B, N, N] dense float64 weight matrix = the reference's self.adj (derived by
+                                              ge_build_adjacency), used when N <= 64 by the kinds stepping in fp64; or NULL */
 
     /* ---- instance parameters (static) ---- */
     int32_t *src, *dest;          /* [B] */
@@ -121,6 +123,9 @@ typedef struct ge_batch {
     double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
     uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
                                               same recurrence as oracle/graphenvs_oracle.c oenv_rollout */
+    uint32_t *step_count;         /* [1]      device counter of ge_step launches, or NULL.  ge_step increments it,
+                                              ge_sample_actions adds it to `t`: lets a captured CUDA graph (frozen
+                                              kernel arguments) draw fresh actions on every replay */
 } ge_batch;
 
 /* step outputs (device pointers) */
@@ -158,7 +163,9 @@ int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *
 
 /* End-to-end entry with HOST buffers: copies actions H2D, steps, copies reward / flags /
  * solution_cost (and the byte mask [B, AP] when h_mask != NULL, the packed mask [B, AW] when
- * h_mask_bits != NULL) D2H, and synchronises the stream.
+ * h_mask_bits != NULL) D2H, and synchronises the stream.  If reward | flags | solution_cost |
+ * mask_bits are laid out back to back in that order on the device AND on the host (B even), the
+ * results come back in one copy.
  * d_actions / out are device staging buffers owned by the caller. */
 int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                  float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
