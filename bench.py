@@ -166,6 +166,7 @@ def cpu_rate(wl, budget_s, n_envs=None):
     t_gen = time.time()
     envs, orc = cpu_sample_envs(wl, n_envs)
     t_gen = time.time() - t_gen
+    cores = orc.set_threads(0)        # all host threads (torchrun exports OMP_NUM_THREADS=1)
     orc.rollout(envs, 2, SEED, t0=0)  # warm-up (page in, spawn the OpenMP team)
     t, steps = 2, 0
     t0 = time.perf_counter()
@@ -176,7 +177,6 @@ def cpu_rate(wl, budget_s, n_envs=None):
         if time.perf_counter() - t0 >= budget_s:
             break
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": n_envs * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d host-generated envs x %d passes (%.1f s; instance generation %.1f s untimed), oracle/graphenvs_oracle.c "
                       "OpenMP over envs" % (n_envs, steps, dt, t_gen)}
@@ -190,6 +190,7 @@ def run_reference(args):
     env_id, N, E, kw, B, _, desc = WORKLOADS[wl]
     n_envs = int(min(B, max(64, 4_000_000 // (N * N + 2 * E))))
     envs, orc = cpu_sample_envs(wl, n_envs)
+    cores = orc.set_threads(0)        # all host threads (torchrun exports OMP_NUM_THREADS=1)
     t = 0
     for _ in range(max(args.warmup, 1)):
         orc.rollout(envs, 1, SEED, t0=t)
@@ -199,7 +200,6 @@ def run_reference(args):
         orc.rollout(envs, 1, SEED, t0=t)
         t += 1
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     val = n_envs * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -240,16 +240,29 @@ def run_ours(args):
     lib_bytes = layout_bytes_per_step(env)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    env.enable_step_counter()   # device-side t for the sampler: captured launches draw fresh actions every replay
+    env.enable_env_clock()      # per-env t for the sampler: captured launches draw fresh actions every replay
+    fused = args.mode == "fused"
+
+    flush_rd = torch.empty(256 << 20, dtype=torch.uint8, device=dev).view(torch.int64) if args.flush == "write+read" else None
+    sink = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def flush_l2():
+        flush.fill_(1)                        # evicts the working set (write a buffer larger than L2) ...
+        if flush_rd is not None:
+            torch.sum(flush_rd, dim=(0,), out=sink)    # ... then a read pass evicts the DIRTY flush lines, so the timed kernels
+                                              # do not pay for writing the flush buffer back to HBM
 
     def one_step(ev=None):
-        flush.fill_(1)
+        flush_l2()
         if ev:
             ev[0].record()
-        env.sample_actions(SEED, 0)
-        if ev:
-            ev[1].record()
-        env.step_async(env.actions_dev)
+        if fused:                             # action draw + step in one launch (ge_step_sampled):
+            env.step_sampled(SEED, 0)         # the step IS the kernel, no event node in between
+        else:
+            env.sample_actions(SEED, 0)
+            if ev:
+                ev[1].record()
+            env.step_async(env.actions_dev)
         if ev:
             ev[2].record()
 
@@ -279,7 +292,7 @@ def run_ours(args):
         graph.replay()
         torch.cuda.synchronize()
         step_ms += [e[0].elapsed_time(e[2]) for e in events]
-        kern_ms += [e[1].elapsed_time(e[2]) for e in events]
+        kern_ms += [e[0 if fused else 1].elapsed_time(e[2]) for e in events]
     if world > 1:
         dist.barrier()
     w1 = time.time()
@@ -308,7 +321,7 @@ def run_ours(args):
     e2e_s = 0.0
     for k in range(3 + Ke):
         h_act.numpy()[:] = host_policy(rng, host_mask())
-        flush.fill_(k & 0xff)
+        flush_l2()
         torch.cuda.synchronize()
         c0 = time.perf_counter()
         env.step_host(h_act, h_rew, h_flg, h_cost, None, h_bits)
@@ -341,12 +354,13 @@ def run_ours(args):
             "dtype": "f64/f32 + bitsets", "data": "synthetic",
             "config": {"workload": desc, "name": wl, "envs_per_gpu": B, "envs_total": B * world,
                        "instances": "device generator ge_generate (connected G(n,m), reference weight law), seed %d" % SEED,
-                       "policy": "uniform valid action, device counter RNG (ge_sample_actions), inside the timed step",
-                       "auto_reset": True, "l2": "256 MiB flush write between timed steps (per-step CUDA events exclude it)",
+                       "policy": "uniform valid action, device counter RNG, inside the timed step (%s)" %
+                                 ("drawn in the step kernel, ge_step_sampled" if fused else "ge_sample_actions + ge_step"),
+                       "auto_reset": True, "l2": "256 MiB flush %s between timed steps (per-step CUDA events exclude it)" % args.flush,
                        "launch": "CUDA graph of %d steps replayed %d times, external event nodes around every step" % (G, K // G),
                        "byte_mask": True},
             "clocks": clocks,
-            "gpu_launches": 2 * K,
+            "gpu_launches": (1 if fused else 2) * K,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "timed": "sum of ge_step_host calls (pinned H2D actions, step kernel, one D2H of reward/flags/"
                              "solution_cost/packed mask, stream sync); host policy between calls untimed"},
@@ -378,6 +392,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "split"],
+                    help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))

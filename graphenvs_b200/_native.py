@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
                                  "-o", LIB_PATH] + _SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("GE_KNOBS"):   # diagnostic build for profiles/knobs.py
+        cmd.insert(1, "-DGE_KNOBS")
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -64,7 +66,7 @@ class GeBatch(C.Structure):
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
         ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P),
-        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("acc", _P), ("traj", _P), ("step_count", _P),
+        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("acc", _P), ("traj", _P), ("env_steps", _P),
     ]
 
 
@@ -73,7 +75,7 @@ class StepOut(C.Structure):
 
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
-           "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_sample_actions", "ge_obs_len",
+           "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
            "ge_obs_flat", "ge_step_host", "ge_stats"]
 
 _lib = None
@@ -104,6 +106,7 @@ def lib():
     L.ge_reset.argtypes = [BP, _P, _P]
     L.ge_step.argtypes = [BP, _P, C.POINTER(StepOut), _P]
     L.ge_sample_actions.argtypes = [BP, C.c_uint64, C.c_uint32, _P, _P]
+    L.ge_step_sampled.argtypes = [BP, C.c_uint64, C.c_uint32, _P, C.POINTER(StepOut), _P]
     L.ge_obs_len.argtypes = [BP]
     L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
     L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]

@@ -101,7 +101,7 @@ class BatchedGraphEnv:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
         T["acc"] = z((4, B), torch.float64)                      # component-major: one stream per statistic
         T["traj"] = z((B,), torch.int64)
-        self.step_count = None  # enable_step_counter(): device counter for CUDA-graph replays
+        self.env_steps = None   # enable_env_clock(): per-env step counts feeding the samplers (CUDA-graph replays)
         # step outputs
         self.reward = self._io[:4 * B].view(torch.float32)
         self.flags = self._io[4 * Bp:4 * Bp + 4 * B].view(B, 4)
@@ -120,13 +120,13 @@ class BatchedGraphEnv:
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
 
-    def enable_step_counter(self):
-        """Device-side launch counter: ge_step increments it, ge_sample_actions adds it to `t`, so a
+    def enable_env_clock(self):
+        """Per-env step counters: ge_step increments them and the samplers add them to `t`, so a
         captured CUDA graph (frozen kernel arguments) draws fresh actions on every replay."""
-        if self.step_count is None:
-            self.step_count = torch.zeros((1,), dtype=torch.int32, device=self.device)
-            self.desc.step_count = self.step_count.data_ptr()
-        return self.step_count
+        if self.env_steps is None:
+            self.env_steps = torch.zeros((self.B,), dtype=torch.int32, device=self.device)
+            self.desc.env_steps = self.env_steps.data_ptr()
+        return self.env_steps
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -310,6 +310,13 @@ class BatchedGraphEnv:
     def step_async(self, actions):
         """Same as step() without building the info dict (bench / rollout loops)."""
         _native.check(self.lib.ge_step(C.byref(self.desc), _ptr(actions), C.byref(self._out), self._stream()))
+
+    def step_sampled(self, seed, t, out=None):
+        """Random-rollout step: uniform valid action drawn in-kernel + step, one launch.  Results as step_async."""
+        out = self.actions_dev if out is None else out
+        _native.check(self.lib.ge_step_sampled(C.byref(self.desc), int(seed), int(t), _ptr(out), C.byref(self._out),
+                                               self._stream()))
+        return out
 
     def sample_actions(self, seed, t, out=None):
         out = self.actions_dev if out is None else out

@@ -41,17 +41,25 @@ static bool uses_adj(int kind) {
 // ------------------------------------------------------------------ kernels
 namespace {
 
-__global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int32_t *__restrict__ actions, ge_step_out out,
-                                                         int words_per_warp) {
+// SAMPLED: draw the action from the current mask inside the kernel (ge_step_sampled) and publish it.
+template <bool SAMPLED>
+__global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
+                                                         int words_per_warp, uint64_t seed, uint32_t t) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
     if (b >= d.B) return;
-    if (b == 0 && lane == 0 && d.step_count) *d.step_count += 1;  // read only by later launches (sampler)
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     EnvPtrs p = env_ptrs(d, b);
     StepRes r;
-    const int a = actions[b];
+    const uint32_t nsteps = d.env_steps ? d.env_steps[b] : 0u;
+    int a;
+    if (SAMPLED) {
+        a = warp_sample(d.mask_bits + (size_t)b * d.AW, d.AW, lane, seed, (uint32_t)(d.env_id0 + b), t + nsteps);
+        if (lane == 0) actions[b] = a;
+    } else {
+        a = actions[b];
+    }
     if (d.done[b]) {  // only reachable with auto-reset off
         r.reward = 0.0; r.sol = __longlong_as_double(0x7ff8000000000000ll);
         r.done = 0; r.solved = -1; r.has_mask = 0; r.status = GE_STEP_AFTER_DONE;
@@ -71,6 +79,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, const int
             d.traj[b] = cs;
         }
         if (r.status == GE_STEP_OK) {
+            if (d.env_steps) d.env_steps[b] = nsteps + 1u;
             d.acc[2 * (size_t)d.B + b] += r.reward;  // [4, B]: the per-step stream is one component wide
             if (r.done) {
                 d.acc[b] += 1.0;
@@ -101,37 +110,8 @@ __global__ void __launch_bounds__(GE_WPB * 32) sample_kernel(ge_batch d, uint64_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
     if (b >= d.B) return;
-    const uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
-    if (d.step_count) t += *d.step_count;
-    int total = 0;
-    for (int w = lane; w < d.AW; w += 32) total += __popc(mb[w]);
-    total = __reduce_add_sync(GE_FULL, total);
-    int action = -1;
-    if (total > 0) {
-        uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t) * (uint64_t)total) >> 32);
-        int before = 0;
-        for (int w0 = 0; w0 < d.AW; w0 += 32) {
-            int w = w0 + lane;
-            uint32_t word = w < d.AW ? mb[w] : 0u;
-            int c = __popc(word), inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int x = __shfl_up_sync(GE_FULL, inc, o);
-                if (lane >= o) inc += x;
-            }
-            int chunk = __shfl_sync(GE_FULL, inc, 31);
-            if ((int)r < before + chunk) {
-                unsigned hit = __ballot_sync(GE_FULL, (int)r < before + inc);
-                int src_lane = __ffs(hit) - 1;
-                int excl = before + inc - c;
-                int pos = (lane == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
-                pos = __shfl_sync(GE_FULL, pos, src_lane);
-                action = ((w0 + src_lane) << 5) + pos;
-                break;
-            }
-            before += chunk;
-        }
-    }
+    if (d.env_steps) t += d.env_steps[b];
+    int action = warp_sample(d.mask_bits + (size_t)b * d.AW, d.AW, lane, seed, (uint32_t)(d.env_id0 + b), t);
     if (lane == 0) actions[b] = action;
 }
 
@@ -363,7 +343,7 @@ __global__ void stats_kernel(ge_batch d, double *out4) {
 
 // lane-per-env kernels for N <= 64 (ge_lane.cu)
 bool ge_lane_eligible(const ge_batch *d);
-int ge_lane_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, cudaStream_t st);
+int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 int ge_lane_sample(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, cudaStream_t st);
 
@@ -498,18 +478,32 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     return GE_OK;
 }
 
-int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, void *stream) {
+static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t,
+                     void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
-    if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, (cudaStream_t)stream);
+    if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
-    if ((rc = set_smem(step_kernel, smem))) return rc;
-    step_kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw);
+    if (sampled) {
+        if ((rc = set_smem(step_kernel<true>, smem))) return rc;
+        step_kernel<true><<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
+    } else {
+        if ((rc = set_smem(step_kernel<false>, smem))) return rc;
+        step_kernel<false><<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, 0, 0);
+    }
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
+}
+
+int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, void *stream) {
+    return step_impl(d, const_cast<int32_t *>(actions), out, false, 0, 0, stream);  // not written when !sampled
+}
+
+int ge_step_sampled(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, const ge_step_out *out, void *stream) {
+    return step_impl(d, actions, out, true, seed, t, stream);
 }
 
 int ge_sample_actions(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, void *stream) {

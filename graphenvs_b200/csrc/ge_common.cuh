@@ -62,6 +62,39 @@ __host__ __device__ inline uint32_t mix32(uint64_t seed, uint32_t env, uint32_t 
     return (uint32_t)(z >> 32);
 }
 
+// Uniform choice among the valid bits of a packed mask (README.md:54-68 loop): the r-th set bit,
+// r = mix32(seed, env, t) * popcount >> 32.  Warp-cooperative; result is warp-uniform, -1 if empty.
+__device__ inline int warp_sample(const uint32_t *mb, int AW, int lane, uint64_t seed, uint32_t env, uint32_t t) {
+    int total = 0;
+    for (int w = lane; w < AW; w += 32) total += __popc(mb[w]);
+    total = __reduce_add_sync(GE_FULL, total);
+    if (total <= 0) return -1;
+    uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
+    int before = 0, action = -1;
+    for (int w0 = 0; w0 < AW; w0 += 32) {
+        int w = w0 + lane;
+        uint32_t word = w < AW ? mb[w] : 0u;
+        int c = __popc(word), inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int x = __shfl_up_sync(GE_FULL, inc, o);
+            if (lane >= o) inc += x;
+        }
+        int chunk = __shfl_sync(GE_FULL, inc, 31);
+        if ((int)r < before + chunk) {
+            unsigned hit = __ballot_sync(GE_FULL, (int)r < before + inc);
+            int src_lane = __ffs(hit) - 1;
+            int excl = before + inc - c;
+            int pos = (lane == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
+            pos = __shfl_sync(GE_FULL, pos, src_lane);
+            action = ((w0 + src_lane) << 5) + pos;
+            break;
+        }
+        before += chunk;
+    }
+    return action;
+}
+
 // Publishes the mask built in shared memory: packed words, optional byte mask; returns popcount.
 __device__ inline int emit_mask(const ge_batch &d, int b, int lane, uint32_t *msk) {
     int cnt = 0;

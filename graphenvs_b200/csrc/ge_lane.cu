@@ -11,13 +11,15 @@
 //
 // Semantics are those of ge_envs.cuh (same reference line map); tests run every N <= 64 case
 // through both paths (GE_FLAG_FORCE_WARP).
+#include <cstdlib>
+
 #include "ge_common.cuh"
 
 using namespace ge;
 
 extern "C" int ge_set_error(int code, const char *fmt, ...);
 
-#define GE_LANE_T 128  // threads (= envs) per block
+#define GE_LANE_T 128  // max threads (= envs) per block; the launch picks blockDim.x (multiple of 32)
 
 namespace {
 
@@ -76,20 +78,80 @@ struct Rows {  // adjacency rows of one env: shared-memory copy (STAGED, explici
     }
 };
 
-// Worklist reachability from `seed` inside `allowed` (seed subset of allowed); stops early once
-// everything in `allowed` is reached.
+// Worklist reachability from `seed` inside `allowed` (seed subset of allowed, one bit); stops early
+// once everything in `allowed` is reached.  Each trip pops up to FOUR frontier nodes -- two from
+// each 32-bit half, so the four find-first-set chains are independent -- and ORs their rows:
+// the four shared-memory loads are in flight together and the dependent chain of a search is
+// ~|reach|/4 trips instead of |reach| (the lane-per-env kernels run at ~4 warps per scheduler,
+// so per-warp latency, not issue rate, is what a step waits for).  An empty slot re-expands the
+// seed, which is harmless.
 template <bool STAGED>
 __device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64 allowed) {
+    const int sidx = __ffsll((long long)seed) - 1;
     u64 reach = seed, frontier = seed;
     while (frontier) {
-        int r = __ffsll((long long)frontier) - 1;
-        frontier &= frontier - 1;
-        u64 nx = R.row(r) & allowed & ~reach;
+        uint32_t lo = (uint32_t)frontier, hi = (uint32_t)(frontier >> 32);
+        uint32_t lo2 = lo & (lo - 1u), hi2 = hi & (hi - 1u);
+        int r0 = lo ? __ffs((int)lo) - 1 : sidx;
+        int r1 = lo2 ? __ffs((int)lo2) - 1 : sidx;
+        int r2 = hi ? 31 + __ffs((int)hi) : sidx;
+        int r3 = hi2 ? 31 + __ffs((int)hi2) : sidx;
+        u64 a = R.row(r0) | R.row(r1);
+        if (R.NW > 1) a |= R.row(r2) | R.row(r3);
+        u64 rest = (u64)(lo2 & (lo2 - 1u)) | ((u64)(hi2 & (hi2 - 1u)) << 32);
+        u64 nx = a & allowed & ~reach;
         reach |= nx;
-        frontier |= nx;
+        frontier = rest | nx;
         if (reach == allowed) break;
     }
     return reach;
+}
+
+// Which of the candidates `cand` are connected to `seed` inside `allowed`?  (LongestPath p>=2:
+// has_path(k, dest) in the residual graph, longest_path.py:137-140.)  Two-sided search: the seed
+// side grows only until every candidate is accounted for, and every still-unknown candidate grows
+// its own component in lock step -- candidates cut off by the visited path sit in tiny fragments
+// that close after a few expansions, so the giant component is never exhausted just to prove a
+// negative.  Mean worklist length at config 2 drops from 21 to 7 rows (30 -> 13 for the slowest
+// lane of a warp), same booleans.
+template <bool STAGED>
+__device__ __forceinline__ u64 connected_candidates(const Rows<STAGED> &R, u64 seed, u64 allowed, u64 cand) {
+    u64 reach = seed, frD = seed;
+    u64 pending = cand & ~reach;
+    while (pending) {
+        const u64 cbit = pending & (~pending + 1ull);
+        u64 comp = cbit, frC = cbit;
+        for (;;) {
+            if (frD) {
+                int r = __ffsll((long long)frD) - 1;
+                frD &= frD - 1;
+                u64 nx = R.row(r) & allowed & ~reach;
+                reach |= nx;
+                frD |= nx;
+                pending &= ~reach;
+                if (!(pending & cbit)) break;            // the seed side reached this candidate
+            }
+            if (frC) {
+                int r = __ffsll((long long)frC) - 1;
+                frC &= frC - 1;
+                u64 nx = R.row(r) & allowed & ~comp;
+                comp |= nx;
+                frC |= nx;
+                if (comp & reach) {                       // touched the seed side: whole fragment is connected
+                    reach |= comp;
+                    frD |= frC;                           // its unexpanded nodes continue on the seed side
+                    pending &= ~reach;
+                    break;
+                }
+            }
+            if (!frC) {                                   // fragment closed without meeting the seed side
+                pending &= ~comp;
+                allowed &= ~comp;
+                break;
+            }
+        }
+    }
+    return cand & reach;
 }
 
 struct LState {
@@ -110,8 +172,10 @@ __device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows<STAGED> &
         if (d.parenting < 2) return m;
         if ((s.vis >> dest) & 1ull) return m;                                  // dest not in alt_G (:135-136)
         u64 allowed = ~s.vis & full;
-        u64 reach = reach_within(R, 1ull << dest, allowed);
-        m &= reach;
+#ifdef GE_KNOBS
+        if (d.flags & 0x100u) return m;
+#endif
+        m &= reach_within(R, 1ull << dest, allowed);
         if (d.parenting == 3 && __popcll(allowed) <= N / 3) m |= allowed;     // :141-143
         return m; }
     case GE_TSP: {                                                             // tsp.py:174-199
@@ -164,6 +228,9 @@ __device__ __forceinline__ void lane_store_state(const ge_batch &d, int b, const
     // mask: packed words + bytes (AP <= 64: up to four 128-bit stores)
     if (d.AW == 1) d.mask_bits[b] = (uint32_t)mask;
     else reinterpret_cast<uint2 *>(d.mask_bits)[b] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+#ifdef GE_KNOBS
+    if (d.flags & 0x400u) return;
+#endif
     if (d.mask_bytes) {
         uint4 *mb = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
         for (int c = 0; c < (d.AP >> 4); ++c) {
@@ -198,8 +265,11 @@ __device__ __forceinline__ Rows<STAGED> stage_rows(const ge_batch &d, int b0, ui
     }
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
+#ifdef GE_KNOBS
+    if (d.flags & 0x200u) { if (threadIdx.x == 0) mbar_expect_tx(bar, 0); R.p = smem + (size_t)threadIdx.x * d.ADJS; R.sp = smem_u32(R.p); return R; }
+#endif
     if (threadIdx.x == 0) {
-        int nenv = min(GE_LANE_T, d.B - b0);
+        int nenv = min((int)blockDim.x, d.B - b0);
         uint32_t bytes = ((uint32_t)nenv * (uint32_t)d.ADJS * 4u + 15u) & ~15u;  // adj_bits carries 16 B of slack
         mbar_expect_tx(bar, bytes);
         bulk_g2s(smem, d.adj_bits + (size_t)b0 * d.ADJS, bytes, bar);
@@ -209,11 +279,22 @@ __device__ __forceinline__ Rows<STAGED> stage_rows(const ge_batch &d, int b0, ui
     return R;
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const int32_t *__restrict__ actions, ge_step_out out) {
+// r-th set bit of a 64-bit mask, r uniform from the counter RNG (same draw as ge_common.cuh:warp_sample).
+__device__ __forceinline__ int lane_sample(u64 m, uint64_t seed, uint32_t env, uint32_t t) {
+    int total = __popcll(m);
+    if (total <= 0) return -1;
+    uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
+    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    int clo = __popc(lo);
+    return (int)r < clo ? (int)__fns(lo, 0, (int)r + 1) : 32 + (int)__fns(hi, 0, (int)r - clo + 1);
+}
+
+template <bool STAGED, bool SAMPLED>
+__global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
+                                                            uint64_t seed, uint32_t t) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
+    const int b0 = blockIdx.x * blockDim.x, b = b0 + threadIdx.x;
     Rows<STAGED> R = stage_rows<STAGED>(d, b0, smem, &bar);
     const bool live = b < d.B;
     const int N = d.N, kind = d.kind;
@@ -225,8 +306,10 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
     double acc_r = 0.0, w_edge = 0.0;
     float w_node = 0.f;
     bool was_done = false;
+    uint32_t nsteps = 0;
     if (live) {
-        a = actions[b];
+        if (!SAMPLED) a = actions[b];
+        if (d.env_steps) nsteps = d.env_steps[b];
         s.vis = load_bits64(d.node_bits, b, d.NW);
         s.aux = d.node_bits2 ? load_bits64(d.node_bits2, b, d.NW) : 0ull;
         s.head = d.head[b];
@@ -234,18 +317,24 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         s.k = 0; s.ecnt = 0;
         if (kind == GE_DENSEST_SUBGRAPH) { int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4); s.k = c.x; s.ecnt = c.y; }
         oldmask = load_bits64(d.mask_bits, b, d.AW);
+        if (SAMPLED) {
+            a = lane_sample(oldmask, seed, (uint32_t)(d.env_id0 + b), t + nsteps);
+            actions[b] = a;
+        }
         was_done = d.done[b] != 0;
         if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) { dest = d.dest[b]; src = d.src[b]; }
         acc_r = d.acc[2 * (size_t)d.B + b];
         if (d.traj) cs = d.traj[b];
         // the one dependent load of the step, issued before waiting for the staged rows
         const bool needs_w = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP;
+#ifdef GE_KNOBS
+        if (!(d.flags & 0x800u))
+#endif
         if (needs_w && a >= 0 && a < N) w_edge = lane_edge_weight(d, b, s.head, a);
         if (kind == GE_MAX_INDEPENDENT_SET && a >= 0 && a < N) w_node = d.node_cost[(size_t)b * N + a];
     }
     if (STAGED) mbar_wait(&bar, 0);
     if (!live) return;
-    if (b == 0 && d.step_count) *d.step_count += 1;  // read only by later launches (sampler)
 
     double reward = 0.0, sol = __longlong_as_double(0x7ff8000000000000ll);
     int done = 0, solved = -1, has_mask = 1, status = GE_STEP_OK;
@@ -265,35 +354,37 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
         const u64 abit = 1ull << a;
         switch (kind) {
         case GE_SHORTEST_PATH: {                                                // shortest_path.py:111-141
+            s.vis |= abit; s.head = a;
+            mask = lane_mask(d, R, s, dest, full);
             double w = w_edge;
             reward = -w;
             s.cost += w;
             if (a == dest) { done = 1; solved = 1; }
-            s.vis |= abit; s.head = a;
-            mask = lane_mask(d, R, s, dest, full);
             if (!done && mask == 0) { done = 1; reward = -(double)N; solved = 0; }
             if (done) sol = s.cost;
             break; }
         case GE_LONGEST_PATH: {                                                 // longest_path.py:147-196
             bool nb = (R.row(s.head) >> a) & 1ull, vis = (s.vis >> a) & 1ull;
             if (d.parenting >= 1 && (!nb || vis)) { status = GE_STEP_INVALID; has_mask = 0; write_state = false; break; }
+            if (nb && !vis) {                                                   // the search first: the weight
+                s.head = a; s.vis |= abit;                                      // load stays in flight behind it
+                mask = lane_mask(d, R, s, dest, full);
+            }
             double w = nb ? w_edge : 0.0;
             reward = w;
             s.cost -= w;
             sol = s.cost;                                                       // every step (:163-165)
             if (!nb || vis) { done = 1; solved = 0; reward = -2.0 * N; has_mask = 0; break; }  // :169-173
-            s.head = a; s.vis |= abit;
             if (a == dest) { done = 1; solved = 1; }
-            mask = lane_mask(d, R, s, dest, full);
             if (!done && mask == 0) { done = 1; reward = -2.0 * N; solved = 0; }
             break; }
         case GE_TSP: {                                                          // tsp.py:213-258
+            s.vis |= abit; s.head = a;
+            mask = lane_mask(d, R, s, dest, full);
             double w = w_edge;
             reward = 0.0 - w;
             s.cost += w;
-            s.vis |= abit; s.head = a;
             if (__popcll(s.vis) == N && a == 0) { done = 1; solved = 1; }
-            mask = lane_mask(d, R, s, dest, full);
             if (!done && mask == 0) { done = 1; reward -= 2.0 * N; solved = 0; }
             if (done) sol = s.cost;
             break; }
@@ -330,6 +421,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, const 
     if (d.traj)
         d.traj[b] = ((cs << 7) | (cs >> 57)) ^ (u64)(uint32_t)a ^ ((u64)done << 40) ^ ((u64)(solved & 3) << 44) ^ ((u64)status << 48);
     if (status == GE_STEP_OK) {
+        if (d.env_steps) d.env_steps[b] = nsteps + 1u;
         d.acc[2 * (size_t)d.B + b] = acc_r + reward;
         if (done) {
             d.acc[b] += 1.0;
@@ -352,7 +444,7 @@ template <bool STAGED>
 __global__ void __launch_bounds__(GE_LANE_T) lane_reset_kernel(ge_batch d, const uint8_t *__restrict__ select) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    const int b0 = blockIdx.x * GE_LANE_T, b = b0 + threadIdx.x;
+    const int b0 = blockIdx.x * blockDim.x, b = b0 + threadIdx.x;
     Rows<STAGED> R = stage_rows<STAGED>(d, b0, smem, &bar);
     const bool live = b < d.B && (!select || select[b]);
     int dest = 0, src = 0;
@@ -374,15 +466,8 @@ __global__ void __launch_bounds__(256) lane_sample_kernel(ge_batch d, uint64_t s
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= d.B) return;
     u64 m = load_bits64(d.mask_bits, b, d.AW);
-    if (d.step_count) t += *d.step_count;
-    int total = __popcll(m), action = -1;
-    if (total > 0) {
-        uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t) * (uint64_t)total) >> 32);
-        uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-        int clo = __popc(lo);
-        action = (int)r < clo ? (int)__fns(lo, 0, (int)r + 1) : 32 + (int)__fns(hi, 0, (int)r - clo + 1);
-    }
-    actions[b] = action;
+    if (d.env_steps) t += d.env_steps[b];
+    actions[b] = lane_sample(m, seed, (uint32_t)(d.env_id0 + b), t);
 }
 
 }  // namespace
@@ -393,30 +478,46 @@ bool ge_lane_eligible(const ge_batch *d) {
            (d->adj_bits != nullptr || d->kind == GE_MAX_INDEPENDENT_SET);
 }
 
-static size_t lane_smem(const ge_batch *d) { return lane_stages(*d) ? (size_t)GE_LANE_T * d->ADJS * 4 + 16 : 0; }
+// Envs per block.  Blocks smaller than the maximum spread the arrival times of the staged copies, so
+// the searches of early blocks overlap the transfers of late ones (single-wave launches otherwise
+// alternate between an all-memory and an all-compute phase).  GE_LANE_T=<32|64|128> overrides.
+static int lane_threads(const ge_batch *d) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("GE_LANE_T");
+        forced = e ? atoi(e) : 0;
+        if (forced != 32 && forced != 64 && forced != 128) forced = 0;
+    }
+    if (forced) return forced;
+    return 64;
+}
+static size_t lane_smem(const ge_batch *d, int T) { return lane_stages(*d) ? (size_t)T * d->ADJS * 4 + 16 : 0; }
 
 int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 template <class K>
 static int lane_prepare(K kernel, size_t smem) { return ge_grant_smem((const void *)kernel, smem); }
 
-int ge_lane_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, cudaStream_t st) {
-    size_t smem = lane_smem(d);
+int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st) {
+    const int T = lane_threads(d);
+    size_t smem = lane_smem(d, T);
     const bool needs_w = d->kind == GE_SHORTEST_PATH || d->kind == GE_LONGEST_PATH || d->kind == GE_TSP;
     if (needs_w && !d->wmat) return ge_set_error(GE_ERR_ARG, "kind %d with N <= 64 needs wmat (ge_build_adjacency fills it)", d->kind);
-    auto kernel = lane_stages(*d) ? lane_step_kernel<true> : lane_step_kernel<false>;
+    auto kernel = lane_stages(*d) ? (sampled ? lane_step_kernel<true, true> : lane_step_kernel<true, false>)
+                                  : (sampled ? lane_step_kernel<false, true> : lane_step_kernel<false, false>);
     int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
-    kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, actions, *out);
+    kernel<<<(d->B + T - 1) / T, T, smem, st>>>(*d, actions, *out, seed, t);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_step_kernel launch: %s", cudaGetErrorString(e));
 }
 
 int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st) {
-    size_t smem = lane_smem(d);
+    const int T = lane_threads(d);
+    size_t smem = lane_smem(d, T);
     auto kernel = lane_stages(*d) ? lane_reset_kernel<true> : lane_reset_kernel<false>;
     int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
-    kernel<<<(d->B + GE_LANE_T - 1) / GE_LANE_T, GE_LANE_T, smem, st>>>(*d, select);
+    kernel<<<(d->B + T - 1) / T, T, smem, st>>>(*d, select);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_reset_kernel launch: %s", cudaGetErrorString(e));
 }

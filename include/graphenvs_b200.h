@@ -26,6 +26,7 @@
  *   ge_generate       instance generation of reset() (shortest_path.py:54-75 and peers) --
  *                     distribution parity only (device RNG), see DESIGN.md
  *   ge_sample_actions README.md:54-68 "random valid action" loop (policy stand-in for benches)
+ *   ge_step_sampled   the same loop body fused: action draw + Env.step() in one launch
  */
 #ifndef GRAPHENVS_B200_H
 #define GRAPHENVS_B200_H
@@ -123,9 +124,9 @@ typedef struct ge_batch {
     double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
     uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
                                               same recurrence as oracle/graphenvs_oracle.c oenv_rollout */
-    uint32_t *step_count;         /* [1]      device counter of ge_step launches, or NULL.  ge_step increments it,
-                                              ge_sample_actions adds it to `t`: lets a captured CUDA graph (frozen
-                                              kernel arguments) draw fresh actions on every replay */
+    uint32_t *env_steps;          /* [B]      per-env count of accepted steps, or NULL.  ge_step increments it and the
+                                              samplers add it to `t`, so a captured CUDA graph (frozen kernel
+                                              arguments) draws fresh actions on every replay */
 } ge_batch;
 
 /* step outputs (device pointers) */
@@ -156,6 +157,9 @@ int ge_generate(const ge_batch *batch, uint64_t seed, int32_t *row_ptr, int32_t 
 int ge_reset(const ge_batch *batch, const uint8_t *select, void *stream);
 int ge_step(const ge_batch *batch, const int32_t *actions, const ge_step_out *out, void *stream);
 int ge_sample_actions(const ge_batch *batch, uint64_t seed, uint32_t t, int32_t *actions, void *stream);
+/* ge_sample_actions + ge_step in ONE launch (random-rollout mode: at these batch sizes a launch costs
+ * as much as the work).  The chosen actions are written to `actions` (may not be NULL). */
+int ge_step_sampled(const ge_batch *batch, uint64_t seed, uint32_t t, int32_t *actions, const ge_step_out *out, void *stream);
 
 /* Reference wire format (utils.py:87-88): out is float32[count, N*F + M*Fe + 2*M]. */
 int ge_obs_len(const ge_batch *batch);

@@ -721,6 +721,20 @@ int oenv_sample_action(const uint8_t *mask, int n, uint64_t seed, uint32_t env, 
     return -1;
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its team size explicitly. */
+int oenv_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* Steps every env `n_steps` times with the sampler above and auto-reset-on-done.
  * Outputs (per env): steps counted, episodes finished, sum of rewards, xor-rotate checksum of
  * (action, done, solved) to compare with the device path.  Uses OpenMP over envs. */

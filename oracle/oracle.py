@@ -64,6 +64,7 @@ def lib():
         L.oenv_sssp_all.argtypes = [P, C.c_int, C.c_double, C.c_int, P]
         L.oenv_sample_action.argtypes = [P, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
         L.oenv_rollout.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, P, P, P]
+        L.oenv_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -152,6 +153,13 @@ class OracleEnv:
 def sample_action(mask, seed, env, t):
     m = np.ascontiguousarray(mask, dtype=np.uint8)
     return lib().oenv_sample_action(_ptr(m), m.shape[0], int(seed), int(env), int(t))
+
+
+def set_threads(n=0):
+    """OpenMP team size of rollout(): n <= 0 -> every CPU this process may run on.  Returns the size in use."""
+    if n <= 0:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return int(lib().oenv_set_threads(int(n)))
 
 
 def rollout(envs, n_steps, seed, env_id0=0, t0=0):

@@ -118,3 +118,37 @@ def test_random_rollout_matches_oracle(cfg, path):
         np.testing.assert_array_equal(obs[b], oe.obs(), err_msg="obs env %d" % b)
     st = env.stats().cpu().numpy()
     assert st[0] >= 1 or T < 30
+
+
+@pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}), ("ShortestPath-v0", 10, 20, {}),
+                                 ("TSP-v0", 40, 120, {"parenting": 2}), ("SteinerTree-v0", 100, 500, {"n_dests": 99}),
+                                 ("MulticastRouting-v0", 120, 600, {"parenting": 4, "n_dests": 5}),
+                                 ("DistributionCenter-v0", 120, 500, {"parenting": 2})],
+                         ids=lambda c: c[0][:-3])
+def test_fused_sampled_step_equals_sample_then_step(cfg):
+    """ge_step_sampled (one launch) == ge_sample_actions + ge_step, bit for bit, including the per-env
+    clock that lets captured graphs draw fresh actions."""
+    env_id, N, E, kw = cfg
+    B, T = 300, 50
+    envs = []
+    for fused in (False, True):
+        e = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+        e.generate(seed=21)
+        e.reset()
+        e.enable_env_clock()
+        acts = []
+        for t in range(T):
+            if fused:
+                acts.append(e.step_sampled(5, 0).clone())
+            else:
+                e.sample_actions(5, 0)
+                acts.append(e.actions_dev.clone())
+                e.step_async(e.actions_dev)
+        torch.cuda.synchronize()
+        envs.append((e, torch.stack(acts)))
+    (a, aa), (b, ab) = envs
+    assert torch.equal(aa, ab)
+    assert len(torch.unique(aa[:, 0])) > 1, "the per-env clock must vary the draws"
+    for name in ("traj", "acc", "mask_bits", "node_bits", "head", "cost"):
+        assert torch.equal(a.t[name], b.t[name]), name
+    assert torch.equal(a.env_steps, b.env_steps) and int(a.env_steps.min()) == T
