@@ -129,8 +129,49 @@ __device__ inline void mask_tsp(const ge_batch &d, const EnvPtrs &p, Scr &s, int
     }
     n_res = __reduce_add_sync(GE_FULL, n_res);
     __syncwarp();
+    // One spanning search of alt_G first (sequential worklist, lane w owns word w of every set): a
+    // node whose expansion discovered nothing is a LEAF of a spanning tree, and removing a leaf
+    // cannot disconnect the graph -- only the tree's internal nodes still need the literal
+    // "remove v, test connectivity" of tsp.py:186-194.  The internal set lives in the (unused by TSP)
+    // distance scratch s.q, because t0..t3 are recycled by the per-candidate searches below.
+    uint32_t *internal = reinterpret_cast<uint32_t *>(s.q);
+    bool have_internal = false;
+    if (n_res >= 2) {
+        int first = 0x7fffffff;
+        for (int w = lane; w < d.NW; w += 32) {
+            internal[w] = 0; s.t1[w] = 0; s.t3[w] = 0;   // internal, frontier, reach
+            if (s.aux[w]) first = min(first, (w << 5) + __ffs(s.aux[w]) - 1);
+        }
+        first = __reduce_min_sync(GE_FULL, first);
+        __syncwarp();
+        if (lane == 0) { s.t1[first >> 5] = 1u << (first & 31); s.t3[first >> 5] = 1u << (first & 31); }
+        __syncwarp();
+        int reached = 1;
+        while (reached < n_res) {
+            int r = 0x7fffffff;  // next frontier node (lowest id)
+            for (int w = lane; w < d.NW; w += 32)
+                if (s.t1[w]) r = min(r, (w << 5) + __ffs(s.t1[w]) - 1);
+            r = __reduce_min_sync(GE_FULL, r);
+            if (r == 0x7fffffff) break;  // frontier empty: alt_G is disconnected
+            int added = 0;
+            for (int w = lane; w < d.NW; w += 32) {
+                uint32_t nx = p.adj[(size_t)r * d.NW + w] & s.aux[w] & ~s.t3[w];
+                uint32_t f = s.t1[w] | nx;
+                if (w == (r >> 5)) f &= ~(1u << (r & 31));
+                s.t1[w] = f;
+                s.t3[w] |= nx;
+                added += __popc(nx);
+            }
+            added = __reduce_add_sync(GE_FULL, added);
+            if (added && lane == 0) internal[r >> 5] |= 1u << (r & 31);
+            reached += added;
+            __syncwarp();
+        }
+        have_internal = reached == n_res;
+    }
     for (int cw = 0; cw < d.NW; ++cw) {
         uint32_t cand = s.msk[cw];  // snapshot of valid_nodes for this word (entries only clear themselves)
+        if (have_internal) cand &= internal[cw] | (cw == 0 ? 1u : 0u);
         while (cand) {
             int v = (cw << 5) + __ffs(cand) - 1;
             cand &= cand - 1;

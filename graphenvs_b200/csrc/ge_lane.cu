@@ -185,6 +185,21 @@ __device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows<STAGED> &
         u64 res = ~s.vis & full & ~1ull;                                       // alt_G = all - start - taken
         int n_res = __popcll(res);
         u64 cand = m;
+        // One spanning search of alt_G first: a node whose expansion discovered nothing is a LEAF of
+        // a spanning tree, and removing a leaf cannot disconnect the graph -- only the tree's
+        // internal nodes still need the literal "remove v, test connectivity" of tsp.py:186-194.
+        if (n_res >= 2) {
+            u64 seed = res & (~res + 1ull), reach = seed, frontier = seed, internal = 0;
+            while (frontier && reach != res) {
+                int r = __ffsll((long long)frontier) - 1;
+                frontier &= frontier - 1;
+                u64 nx = R.row(r) & res & ~reach;
+                if (nx) internal |= 1ull << r;
+                reach |= nx;
+                frontier |= nx;
+            }
+            if (reach == res) cand &= internal | 1ull;   // (bit 0 = start is skipped below anyway)
+        }
         while (cand) {
             int v = __ffsll((long long)cand) - 1;
             cand &= cand - 1;
