@@ -67,6 +67,14 @@ class BatchedGraphEnv:
             T["adj_bits"] = self._adj_store[:B * d.ADJS].view(B, d.ADJS)
             if N <= 64 and self.spec.step_w == "f64":
                 T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
+        par = int(P.get("parenting", -1))
+        if not force_warp:   # derived / state arrays of the incremental-mask kernels (csrc/ge_incr.cu)
+            if env_id == "SteinerTree-v0" or (env_id == "MulticastRouting-v0" and par == 2):
+                T["rev"] = z((B, d.MP), torch.int32)
+            if env_id == "MulticastRouting-v0" and par >= 2:
+                T["esrc"] = z((B, d.MP), torch.int32)
+            if env_id == "MulticastRouting-v0" and par >= 3:
+                T["bestkey"] = z((B, N), torch.int64)
         T["src"] = z((B,), torch.int32)
         T["dest"] = z((B,), torch.int32)
         if self.spec.has_targets:
@@ -114,7 +122,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
             t = self.t.get(name)
@@ -221,7 +229,7 @@ class BatchedGraphEnv:
     def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None):
         """Derived static data after the CSR arrays are in place (load_instances / generate)."""
         L, d = self.lib, self.desc
-        if self.spec.uses_adj:
+        if self.spec.uses_adj or "rev" in self.t or "esrc" in self.t:
             _native.check(L.ge_build_adjacency(C.byref(d), self._stream()))
         what = 0
         if prepare and self.env_id == "DistributionCenter-v0" and d.parenting == 2:

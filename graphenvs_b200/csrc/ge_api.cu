@@ -120,9 +120,24 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
     if (b >= d.B) return;
-    uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
     const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
     const int32_t *col = d.col + (size_t)b * d.MP;
+    if (d.esrc || d.rev) {  // edge-indexed derived arrays of the incremental kernels (ge_incr.cu)
+        int32_t *esrc = d.esrc ? d.esrc + (size_t)b * d.MP : nullptr;
+        int32_t *rev = d.rev ? d.rev + (size_t)b * d.MP : nullptr;
+        for (int u = lane; u < d.N; u += 32)
+            for (int e = rp[u]; e < rp[u + 1]; ++e) {
+                if (esrc) esrc[e] = u;
+                if (rev) {
+                    int v = col[e], r = -1;
+                    for (int k = rp[v]; k < rp[v + 1]; ++k)
+                        if (col[k] == u) { r = k; break; }
+                    rev[e] = r;
+                }
+            }
+    }
+    if (!d.adj_bits) return;
+    uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
     for (int i = lane; i < d.ADJS; i += 32) adj[i] = 0;
     __syncwarp();
     __threadfence_block();
@@ -346,6 +361,10 @@ bool ge_lane_eligible(const ge_batch *d);
 int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 int ge_lane_sample(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, cudaStream_t st);
+// incremental-mask kernels (ge_incr.cu)
+bool ge_incr_eligible(const ge_batch *d);
+int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
+int ge_incr_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
 static int check_batch(const ge_batch *d) {
@@ -415,7 +434,7 @@ int ge_step_smem_bytes(const ge_batch *d) { return scratch_words(*d) * GE_WPB * 
 int ge_build_adjacency(const ge_batch *d, void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
-    if (!d->adj_bits) return fail(GE_ERR_ARG, "adj_bits is null");
+    if (!d->adj_bits && !d->rev && !d->esrc) return fail(GE_ERR_ARG, "no derived array requested (adj_bits / rev / esrc are null)");
     adjacency_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, 0, (cudaStream_t)stream>>>(*d);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
@@ -469,6 +488,7 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     if (rc) return rc;
     if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
     if (ge_lane_eligible(d)) return ge_lane_reset(d, select, (cudaStream_t)stream);
+    if (ge_incr_eligible(d)) return ge_incr_reset(d, select, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -484,6 +504,7 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
     if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
+    if (ge_incr_eligible(d)) return ge_incr_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;

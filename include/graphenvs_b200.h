@@ -96,6 +96,8 @@ typedef struct ge_batch {
     const float *w32;             /* [B, MP]   edge feature column 0 (float32), kinds stepping in fp32 */
     const double *w64;            /* [B, MP]   float64 edge attribute, kinds stepping in fp64 / prepare */
     uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived); allocate 16 B of slack */
+    int32_t *rev;                 /* [B, MP]   index of the reverse edge (v->u) of every edge (u->v) (derived), or NULL */
+    int32_t *esrc;                /* [B, MP]   source node of every edge (derived), or NULL */
     double *wmat;                 /* [B, N, N] dense float64 weight matrix = the reference's self.adj (derived by
                                               ge_build_adjacency), used when N <= 64 by the kinds stepping in fp64; or NULL */
 
@@ -116,8 +118,11 @@ typedef struct ge_batch {
     uint32_t *node_bits2;         /* [B, NW]  DistCenter IS_COVERED; Densest neighbour-union */
     uint32_t *edge_bits;          /* [B, MW]  Multicast EDGE_IS_TAKEN */
     float *dist32;                /* [B, N]   Multicast DISTANCE_FROM_SOURCE column */
+    uint64_t *bestkey;            /* [B, N]   Multicast parenting >= 3: running argmin per frontier vertex,
+                                              (float32 bits of dist[src e] + delay[e]) << 32 | e, ~0 = none; or NULL */
     double *cost;                 /* [B]      running solution_cost (fp32 kinds keep a float value in it) */
-    int32_t *counters;            /* [B, 4]   k_taken, edge_cnt, constraints_satisfied, steps */
+    int32_t *counters;            /* [B, 4]   Densest: k_taken, edge_cnt.  Incremental kernels (ge_incr.cu): targets in the
+                                              tree / nodes taken, popcount of the mask, constraints satisfied */
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
@@ -144,6 +149,7 @@ int ge_fill_layout(ge_batch *batch);
 /* Bytes of dynamic shared memory one step launch uses (for diagnostics / occupancy reports). */
 int ge_step_smem_bytes(const ge_batch *batch);
 
+/* Fills every DERIVED graph array whose pointer is set: adj_bits, wmat, rev, esrc. */
 int ge_build_adjacency(const ge_batch *batch, void *stream);
 /* what: bit0 heuristics (SSSP / MST where the reference's value is tie-independent),
  *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw),

@@ -9,6 +9,17 @@ import golden_util as gu
 LANE_KINDS = ("ShortestPath-v0", "LongestPath-v0", "TSP-v0", "MaxIndependentSet-v0", "DensestSubgraph-v0")
 
 
+def has_fast_path(env_id, n_nodes, parenting=None):
+    """True when the default dispatch is NOT the full-recompute warp-per-env kernel (lane-per-env for
+    N <= 64 node-action kinds, incremental-mask kernels for SteinerTree / Multicast p>=2 / MIS), i.e.
+    when force_warp=True exercises a different code path worth testing."""
+    if n_nodes <= 64 and env_id in LANE_KINDS:
+        return True
+    if env_id == "SteinerTree-v0" or env_id == "MaxIndependentSet-v0":
+        return True
+    return env_id == "MulticastRouting-v0" and (parenting is None or parenting >= 2)
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:12]
 

@@ -15,7 +15,7 @@ GROUPS = cu.grouped_cases()
 @pytest.mark.parametrize("key", list(GROUPS), ids=["-".join(str(x) for x in k) for k in GROUPS])
 def test_replay_group(key, path):
     cases = GROUPS[key]
-    if path == "warp" and not (key[1] <= 64 and key[0] in cu.LANE_KINDS):
+    if path == "warp" and not cu.has_fast_path(key[0], key[1], key[3]):
         pytest.skip("warp-per-env is already the auto path here")
     env = cu.batch_from_cases(cases, force_warp=(path == "warp"))
     B = len(cases)

@@ -50,7 +50,7 @@ CONFIGS = [
 @pytest.mark.parametrize("path", ["auto", "warp"])
 def test_random_rollout_matches_oracle(cfg, path):
     env_id, N, E, kw, T = cfg
-    if path == "warp" and not (N <= 64 and env_id in cu.LANE_KINDS):
+    if path == "warp" and not cu.has_fast_path(env_id, N, kw.get("parenting")):
         pytest.skip("warp-per-env is already the auto path here")
     B, seed = 150, 7   # not a multiple of the 128-env block of the lane kernels
     env = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, force_warp=(path == "warp"), **kw)
