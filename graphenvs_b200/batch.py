@@ -75,6 +75,8 @@ class BatchedGraphEnv:
                 T["esrc"] = z((B, d.MP), torch.int32)
             if env_id == "MulticastRouting-v0" and par >= 3:
                 T["bestkey"] = z((B, N), torch.int64)
+        if env_id == "DistributionCenter-v0":
+            T["wmin"] = z((B,), torch.float64)
         T["src"] = z((B,), torch.int32)
         T["dest"] = z((B,), torch.int32)
         if self.spec.has_targets:
@@ -122,7 +124,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
             t = self.t.get(name)
@@ -229,7 +231,7 @@ class BatchedGraphEnv:
     def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None):
         """Derived static data after the CSR arrays are in place (load_instances / generate)."""
         L, d = self.lib, self.desc
-        if self.spec.uses_adj or "rev" in self.t or "esrc" in self.t:
+        if self.spec.uses_adj or "rev" in self.t or "esrc" in self.t or "wmin" in self.t:
             _native.check(L.ge_build_adjacency(C.byref(d), self._stream()))
         what = 0
         if prepare and self.env_id == "DistributionCenter-v0" and d.parenting == 2:

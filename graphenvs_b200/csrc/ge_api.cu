@@ -136,6 +136,13 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
                 }
             }
     }
+    if (d.wmin && d.w64) {
+        const double *w64 = d.w64 + (size_t)b * d.MP;
+        double m = __longlong_as_double(0x7ff0000000000000ll);
+        for (int e = lane; e < d.M; e += 32) m = fmin(m, w64[e]);
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(GE_FULL, m, o));
+        if (lane == 0) d.wmin[b] = m;
+    }
     if (!d.adj_bits) return;
     uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
     for (int i = lane; i < d.ADJS; i += 32) adj[i] = 0;
@@ -434,7 +441,7 @@ int ge_step_smem_bytes(const ge_batch *d) { return scratch_words(*d) * GE_WPB * 
 int ge_build_adjacency(const ge_batch *d, void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
-    if (!d->adj_bits && !d->rev && !d->esrc) return fail(GE_ERR_ARG, "no derived array requested (adj_bits / rev / esrc are null)");
+    if (!d->adj_bits && !d->rev && !d->esrc && !d->wmin) return fail(GE_ERR_ARG, "no derived array requested (adj_bits / rev / esrc / wmin are null)");
     adjacency_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, 0, (cudaStream_t)stream>>>(*d);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;

@@ -148,48 +148,42 @@ __device__ inline int edge_src(const int32_t *rp, int N, int e) {
 // For every node u in `set` (NW words, in shared memory) and every edge e of row u, calls
 //     f(owner_lane, e, active)
 // from ALL 32 lanes (so f may shuffle); `owner_lane` is the lane that holds the per-node payload
-// the caller loaded in `load(u)`; `active` is false for padding lanes.  Up to 32 rows are in
-// flight at once, their edges are walked 32 per iteration in row order => coalesced segments,
-// high memory-level parallelism, no per-row serial latency chain.
+// the caller loaded in `load(u)`; `active` is false for padding lanes.  The 32 nodes of one set
+// word are handled together: lane l owns node 32w+l (row bounds = two coalesced 128-byte loads),
+// an inclusive scan of the row lengths lays the edges of all member rows out on one line, and each
+// group of 32 consecutive edge slots finds its owning row with a 5-step shuffle binary search.
+// Edges are walked in row order => coalesced segments, up to 32 rows in flight, no per-row serial
+// latency chain, and no find-nth-set-bit (ncu: __fns was 25-30 % of the instructions of the first
+// version, profiles/r01_step_kernel_cfg5_distcenter_warp_v1.md).
 template <class Load, class Visit>
 __device__ inline void expand_set(const int32_t *rp, const uint32_t *set, int NW, int lane, Load load, Visit f) {
     for (int w = 0; w < NW; ++w) {
-        uint32_t bits = set[w];  // warp-uniform (broadcast read)
+        const uint32_t bits = set[w];  // warp-uniform (broadcast read)
         if (!bits) continue;
-        int nn = __popc(bits);
-        int u = -1, lo = 0, len = 0;
-        if (lane < nn) {
-            u = (w << 5) + (int)__fns(bits, 0, lane + 1);
-            lo = rp[u];
-            len = rp[u + 1] - lo;
-        }
-        // compact away empty rows so that row starts below are distinct
-        unsigned ne = __ballot_sync(GE_FULL, len > 0);
-        int n2 = __popc(ne);
-        int from = lane < n2 ? (int)__fns(ne, 0, lane + 1) : lane;
-        u = __shfl_sync(GE_FULL, u, from);
-        lo = __shfl_sync(GE_FULL, lo, from);
-        len = __shfl_sync(GE_FULL, len, from);
-        if (lane >= n2) { u = -1; len = 0; }
-        load(u);  // caller captures payload for node u in registers of this lane
-        int pre = len;  // inclusive scan
+        const bool member = (bits >> lane) & 1u;
+        const int u = (w << 5) + lane;
+        int lo = 0, len = 0;
+        if (member) { lo = rp[u]; len = rp[u + 1] - lo; }
+        load(member ? u : -1);  // caller captures payload for node u in registers of this lane
+        int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(GE_FULL, pre, o);
-            if (lane >= o) pre += t;
+            int t = __shfl_up_sync(GE_FULL, incl, o);
+            if (lane >= o) incl += t;
         }
-        int total = __shfl_sync(GE_FULL, pre, 31);
-        pre -= len;  // exclusive
-        int base = lo - pre;
+        const int total = __shfl_sync(GE_FULL, incl, 31);
+        const int base = lo - (incl - len);  // edge id = base + slot for the slots of this lane's row
         for (int t0 = 0; t0 < total; t0 += 32) {
-            uint32_t st = (len > 0 && pre >= t0 && pre < t0 + 32) ? (1u << (pre - t0)) : 0u;
-            st = __reduce_or_sync(GE_FULL, st);
-            int before = __popc(__ballot_sync(GE_FULL, len > 0 && pre < t0));
-            int owner = before + __popc(st & (0xffffffffu >> (31 - lane))) - 1;
-            int t = t0 + lane;
-            bool active = t < total;
-            int ob = __shfl_sync(GE_FULL, base, owner & 31);
-            f(owner & 31, ob + t, active);
+            const int t = t0 + lane;
+            int owner = 0;  // first lane whose inclusive prefix exceeds t
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                int v = __shfl_sync(GE_FULL, incl, owner + step - 1);
+                if (v <= t) owner += step;
+            }
+            owner &= 31;
+            const int ob = __shfl_sync(GE_FULL, base, owner);
+            f(owner, ob + t, t < total);
         }
     }
 }
@@ -204,6 +198,10 @@ __device__ inline void sssp_warp(const ge_batch &d, int b, int lane, Scr &s, int
     const int32_t *col = d.col + (size_t)b * d.MP;
     const double *w64 = d.w64 + (size_t)b * d.MP;
     const u64 INF = 0x7ff0000000000000ull;
+    // A node whose distance plus the instance's SMALLEST weight already exceeds the cutoff cannot relax
+    // anything (fp64 add is monotone in the weight), so it never enters the frontier: with cutoff 1.0
+    // and weights k/10 >= 0.3 only nodes within 0.7 are expanded.  Exact, not a heuristic.
+    const double wmin = (use_cutoff && d.wmin) ? d.wmin[b] : 0.0;
     for (int v = lane; v < d.N; v += 32) s.q[v] = INF;
     for (int w = lane; w < d.NW; w += 32) { s.t0[w] = 0; s.t1[w] = 0; }
     __syncwarp();
@@ -221,7 +219,7 @@ __device__ inline void sssp_warp(const ge_batch &d, int b, int lane, Scr &s, int
                     if (!use_cutoff || nd <= cutoff) {
                         u64 nb = (u64)__double_as_longlong(nd);
                         u64 old = atomicMin(&s.q[v], nb);
-                        if (nb < old) atomicOr(&s.t1[v >> 5], 1u << (v & 31));
+                        if (nb < old && (!use_cutoff || nd + wmin <= cutoff)) atomicOr(&s.t1[v >> 5], 1u << (v & 31));
                     }
                 }
             });
