@@ -329,17 +329,10 @@ __global__ void __launch_bounds__(GE_WPB * 32) prep_inrange_kernel(ge_batch d, i
     const int b = (int)(job / d.n_targets), t = (int)(job % d.n_targets);
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     int node = d.targets[(size_t)b * d.n_targets + t];
-    sssp_warp(d, b, lane, s, node, d.max_distance, true);
+    sssp_cutoff_warp(d, b, lane, s, node, d.max_distance);
     __syncwarp();
     uint32_t *row = d.in_range + ((size_t)b * d.n_targets + t) * d.NW;
-    for (int w = lane; w < d.NW; w += 32) {
-        uint32_t bits = 0;
-        for (int j = 0; j < 32; ++j) {
-            int v = (w << 5) + j;
-            if (v < d.N && s.q[v] != 0x7ff0000000000000ull) bits |= 1u << j;
-        }
-        row[w] = bits;
-    }
+    for (int w = lane; w < d.NW; w += 32) row[w] = s.t2[w];
 }
 
 __global__ void stats_kernel(ge_batch d, double *out4) {

@@ -23,10 +23,12 @@ struct Scr {
     uint32_t *aux;  // [NW] second node set (covered, neighbour-union, residual ...)
     uint32_t *t0, *t1, *t2, *t3;  // [NW] temporaries (frontier / next / reach / candidates)
     uint32_t *msk;  // [AW] mask under construction
+    uint16_t *lst;  // [2N] two frontier node lists of the cutoff SSSP (DistributionCenter only)
 };
 
 __host__ __device__ inline int scratch_words(const ge_batch &d) {
     int w = 2 * d.N + 6 * d.NW + d.AW;
+    if (d.kind == GE_DISTRIBUTION_CENTER) w += d.N;  // two uint16 node lists
     return (w + 3) & ~3;  // keep every warp slice 16-byte aligned
 }
 
@@ -40,7 +42,8 @@ __device__ inline Scr carve(uint32_t *base, const ge_batch &d) {
     s.t1 = p; p += d.NW;
     s.t2 = p; p += d.NW;
     s.t3 = p; p += d.NW;
-    s.msk = p;
+    s.msk = p; p += d.AW;
+    s.lst = reinterpret_cast<uint16_t *>(p);
     return s;
 }
 
@@ -228,6 +231,90 @@ __device__ inline void sssp_warp(const ge_batch &d, int b, int lane, Scr &s, int
         for (int w = lane; w < d.NW; w += 32) { uint32_t n = s.t1[w]; s.t0[w] = n; s.t1[w] = 0; any |= n; }
         __syncwarp();
         if (!__any_sync(GE_FULL, any != 0)) break;
+    }
+}
+
+// Cutoff SSSP from one node (find_nodes_in_range, distribution_center.py:25-26 =
+// nx.single_source_dijkstra_path_length(cutoff=...), nx:algorithms/shortest_paths/weighted.py:853-881):
+// leaves in s.t2 the set of nodes whose fp64 left-fold distance is <= cutoff.  Label-correcting rounds
+// over a compact LIST of frontier nodes (a ball of radius 1.0 under weights >= 0.3 has a few dozen
+// expandable nodes scattered over all 16 set words -- a bitset frontier would walk 16 mostly empty words
+// per round).  Up to 32 frontier rows are laid out on one line by an inclusive scan and consumed 32
+// edges at a time (shuffle binary search for the owning row).  64-bit shared-memory atomicMin is a CAS
+// spin on this hardware (SASS ATOMS.CAST.SPIN.64), so a plain read filters the relaxations that cannot
+// improve anything before the atomic.  Uses s.q (distances), s.t0 (queued-for-next-round), s.t1[0]
+// (next-round count), s.lst.
+__device__ inline void sssp_cutoff_warp(const ge_batch &d, int b, int lane, Scr &s, int source, double cutoff) {
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    const double *w64 = d.w64 + (size_t)b * d.MP;
+    const u64 INF = 0x7ff0000000000000ull;
+    const double wmin = d.wmin ? d.wmin[b] : 0.0;  // see sssp_warp: exact pruning of nodes that cannot relax anything
+    const int N = d.N;
+    uint16_t *cur = s.lst, *nxt = s.lst + N;
+    int *cnt = reinterpret_cast<int *>(s.t1);
+    for (int v = lane; v < N; v += 32) s.q[v] = INF;
+    for (int w = lane; w < d.NW; w += 32) { s.t0[w] = 0; s.t2[w] = 0; }
+    __syncwarp();
+    if (lane == 0) { s.q[source] = 0ull; s.t2[source >> 5] = 1u << (source & 31); cur[0] = (uint16_t)source; *cnt = 0; }
+    __syncwarp();
+    int ncur = (0.0 + wmin <= cutoff) ? 1 : 0;
+    while (ncur > 0) {
+        for (int base0 = 0; base0 < ncur; base0 += 32) {
+            const int i = base0 + lane;
+            int lo = 0, len = 0;
+            double du = 0.0;
+            if (i < ncur) {
+                int u = cur[i];
+                lo = rp[u];
+                len = rp[u + 1] - lo;
+                du = __longlong_as_double((long long)s.q[u]);
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(GE_FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(GE_FULL, incl, 31);
+            const int rbase = lo - (incl - len);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                int owner = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    int x = __shfl_sync(GE_FULL, incl, owner + step - 1);
+                    if (x <= t) owner += step;
+                }
+                owner &= 31;
+                const int e = __shfl_sync(GE_FULL, rbase, owner) + t;
+                const double dsrc = __shfl_sync(GE_FULL, du, owner);
+                if (t < total) {
+                    const int v = col[e];
+                    const double nd = dsrc + w64[e];
+                    if (nd <= cutoff) {                                     // nx: skip when dist + w > cutoff
+                        const u64 nb = (u64)__double_as_longlong(nd);
+                        if (nb < s.q[v]) {
+                            const u64 old = atomicMin(&s.q[v], nb);
+                            if (nb < old) {
+                                if (old == INF) atomicOr(&s.t2[v >> 5], 1u << (v & 31));
+                                if (nd + wmin <= cutoff) {
+                                    const uint32_t bit = 1u << (v & 31);
+                                    if (!(atomicOr(&s.t0[v >> 5], bit) & bit)) nxt[atomicAdd(cnt, 1)] = (uint16_t)v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        ncur = *cnt;
+        __syncwarp();
+        if (lane == 0) *cnt = 0;
+        for (int w = lane; w < d.NW; w += 32) s.t0[w] = 0;
+        uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+        __syncwarp();
     }
 }
 

@@ -283,21 +283,41 @@ __device__ inline void mask_distribution_center(const ge_batch &d, const EnvPtrs
     }
     const int32_t *tg = d.targets + (size_t)b * d.n_targets;
     const uint32_t *ir = d.in_range + (size_t)b * d.n_targets * d.NW;
-    uint32_t acc[4] = {0, 0, 0, 0};  // lane owns words lane, lane+32, ... (N <= 4096)
+    // 1. compact the uncovered targets into a list (s.lst: free again once the step's SSSP is done)
+    uint16_t *live = s.lst;
+    int nlive = 0;
     for (int t0 = 0; t0 < d.n_targets; t0 += 32) {
         int t = t0 + lane;
-        bool unc = false;
-        if (t < d.n_targets) unc = !tbit(s.aux, tg[t]);
-        unsigned live = __ballot_sync(GE_FULL, unc);
-        while (live) {
-            int tt = t0 + __ffs(live) - 1;
-            live &= live - 1;
-            int k = 0;
-            for (int w = lane; w < d.NW; w += 32, ++k) acc[k] |= ir[(size_t)tt * d.NW + w];
+        bool unc = t < d.n_targets && !tbit(s.aux, tg[t]);
+        unsigned bal = __ballot_sync(GE_FULL, unc);
+        if (unc) live[nlive + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
+        nlive += __popc(bal);
+    }
+    __syncwarp();
+    // 2. OR their in-range rows.  A row is NW words: 32/L rows are read per pass by groups of L lanes, four
+    //    passes are issued back to back (independent loads) -- a one-row-at-a-time loop serialised
+    //    ~100 dependent-latency loads per step and was the largest single cost of this kernel.
+    const int L = d.NW <= 1 ? 1 : d.NW <= 2 ? 2 : d.NW <= 4 ? 4 : d.NW <= 8 ? 8 : d.NW <= 16 ? 16 : 32;
+    const int rpp = 32 / L, grp = lane / L, wl = lane % L;
+    uint32_t acc[4] = {0, 0, 0, 0};  // lane owns words wl, wl+L, ... (N <= 4096)
+    for (int i0 = 0; i0 < nlive; i0 += 4 * rpp) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int idx = i0 + j * rpp + grp;
+            if (idx < nlive) {
+                const uint32_t *row = ir + (size_t)live[idx] * d.NW;
+                int k = 0;
+                for (int w = wl; w < d.NW; w += L, ++k) acc[k] |= __ldg(row + w);
+            }
         }
     }
-    int k = 0;
-    for (int w = lane; w < d.NW; w += 32, ++k) s.msk[w] = acc[k] & ~s.vis[w];
+    for (int o = L; o < 32; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] |= __shfl_xor_sync(GE_FULL, acc[k], o);
+    if (grp == 0) {
+        int k = 0;
+        for (int w = wl; w < d.NW; w += L, ++k) s.msk[w] = acc[k] & ~s.vis[w];
+    }
     __syncwarp();
 }
 
@@ -555,14 +575,10 @@ __device__ inline void step_env(const ge_batch &d, const EnvPtrs &p, Scr &s, int
         float rew = -w;
         if (lane == 0) s.vis[a >> 5] |= 1u << (a & 31);
         __syncwarp();
-        sssp_warp(d, b, lane, s, a, d.max_distance, true);  // find_nodes_in_range (:25-26,155)
+        sssp_cutoff_warp(d, b, lane, s, a, d.max_distance);  // find_nodes_in_range (:25-26,155) -> s.t2
         int gained = 0;
         for (int wi = lane; wi < d.NW; wi += 32) {
-            uint32_t reach = 0;
-            for (int j = 0; j < 32; ++j) {
-                int v = (wi << 5) + j;
-                if (v < N && s.q[v] != 0x7ff0000000000000ull) reach |= 1u << j;
-            }
+            uint32_t reach = s.t2[wi];
             uint32_t newly = reach & ~s.aux[wi];
             s.aux[wi] |= reach;
             gained += __popc(newly & p.tgt[wi]);
