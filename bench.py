@@ -52,31 +52,49 @@ SEED = 20260101
 
 
 def layout_bytes_per_step(env):
-    """Compulsory HBM bytes per env-step of THIS engine's data layout:
-    state read+write, action in, reward/flags/cost out, packed + byte mask out, statistics r/w,
-    plus the graph bytes the env's rule has to read once."""
+    """Compulsory HBM bytes per env-step of THIS engine's data layout and algorithm:
+    state read+write, action in (or the packed mask the in-kernel sampler scans), reward/flags/cost out,
+    mask delta or mask rewrite, statistics r/w, plus the graph bytes the env's rule has to read once.
+    Useful bytes, not 32-byte sectors: scattered accesses cost more on the wire (see roofline.traffic)."""
     d, N, M = env.desc, env.N, env.M
     nw4 = d.NW * 4
-    fixed = 4 + 4 + 4 + 8 + 2 * (4 + 8 + 1) + 2 * 32 + 2 * 8   # action, reward, flags, sol, head/cost/done rw, acc rw, traj rw
-    mask = d.AW * 4 * 2 + (d.AP if env.t.get("mask_bytes") is not None else 0)  # old mask read, new written, bytes written
-    state = 2 * nw4
+    has_bytes = env.t.get("mask_bytes") is not None
+    fixed = 4 + 4 + 4 + 8 + 2 * (4 + 8 + 1) + 2 * 8 + 2 * 8 + 8   # action, reward, flags, sol, head/cost/done rw, acc[2] rw, traj rw, clock
     deg = M / max(N, 1)
     k = env.env_id
+    incremental = not (d.flags & 8) and (k in ("SteinerTree-v0",) or (k == "MulticastRouting-v0" and d.parenting >= 2)
+                                         or (k == "MaxIndependentSet-v0" and N > 64))
+    if incremental:
+        sample = d.AW * 4                                  # the sampler walks the packed mask
+        if k == "MaxIndependentSet-v0":
+            return float(fixed + sample + 2 * 8 + 4 + 32 + (1 if has_bytes else 0))
+        upd = 2 * deg * (8 + (1 if has_bytes else 0))      # ~deg bits set + ~deg bits cleared (word r/w + byte)
+        graph = 8 + 8 + deg * 8                            # col[a], w[a]; rp[v], rp[v+1]; row(v): col + rev / w
+        state = nw4 + 8 + 4 + 32                           # tree bits read, one word r/w, target word, counters r/w
+        if k == "MulticastRouting-v0":
+            graph += 4 + 4 + 4 + 8 + 4                     # esrc[a], dist[u], dist[v] write, edge bit r/w, max_distance
+            if d.parenting >= 3:
+                graph += deg * (8 + 4)                     # best[x] read (+ write for about half of them)
+        return float(fixed + sample + upd + graph + state)
+    mask = d.AW * 4 * 2 + (d.AP if has_bytes else 0)       # old mask read, new written, bytes written
+    state = 2 * nw4
     if k == "ShortestPath-v0":
-        graph = nw4 + 8 + deg * 4 + 8
-    elif k == "LongestPath-v0":
-        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + 8 + deg * 4 + 8
-    elif k == "TSP-v0":
-        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + 8 + deg * 4 + 8
+        graph = nw4 + 8
+    elif k in ("LongestPath-v0", "TSP-v0"):
+        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + (8 if N <= 64 else 8 + deg * 4 + 8)
     elif k == "SteinerTree-v0":
         graph = 0.5 * (M * 4 + (N + 1) * 4) + 12 + nw4      # rows of tree nodes: on average half of the CSR
     elif k == "MulticastRouting-v0":
         graph = 0.5 * (M * 8 + (N + 1) * 4) + N * 4 + 12 + nw4 + 2 * d.MW * 4
     elif k == "DistributionCenter-v0":
-        graph = M * 12 + (N + 1) * 4 + d.n_targets * (nw4 + 4) + 4 + 2 * nw4
+        # cutoff SSSP ball: with cutoff c and smallest weight w only nodes within c - w are expanded; measured ~22 rows
+        # at N=500 E=4000 c=1 (DESIGN.md); each row = 2 row_ptr + deg * (col 4 + w64 8); + in-range rows of the
+        # still uncovered targets (about half of them on average) + covered/taken/target sets
+        rows = 22 if (N == 500 and M == 8000) else max(1.0, min(N, 1 + deg + deg * deg * 0.06))
+        graph = rows * (8 + deg * 12) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
     elif k == "DensestSubgraph-v0":
         graph = nw4 + 16 + 2 * nw4
-    else:  # MaxIndependentSet
+    else:  # MaxIndependentSet (lane family)
         graph = 4
     return float(fixed + mask + state + graph)
 

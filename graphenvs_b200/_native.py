@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
                                  "-o", LIB_PATH] + _SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("GE_NVCC_DEFS"):   # e.g. GE_NVCC_DEFS="-DGE_INCR_MINB=6" for tuning experiments
+        cmd[1:1] = os.environ["GE_NVCC_DEFS"].split()
     if os.environ.get("GE_KNOBS"):   # diagnostic build for profiles/knobs.py
         cmd.insert(1, "-DGE_KNOBS")
     env = dict(os.environ)

@@ -67,10 +67,15 @@ __host__ __device__ inline uint32_t mix32(uint64_t seed, uint32_t env, uint32_t 
 
 // Uniform choice among the valid bits of a packed mask (README.md:54-68 loop): the r-th set bit,
 // r = mix32(seed, env, t) * popcount >> 32.  Warp-cooperative; result is warp-uniform, -1 if empty.
-__device__ inline int warp_sample(const uint32_t *mb, int AW, int lane, uint64_t seed, uint32_t env, uint32_t t) {
-    int total = 0;
-    for (int w = lane; w < AW; w += 32) total += __popc(mb[w]);
-    total = __reduce_add_sync(GE_FULL, total);
+// `known_total` >= 0: the caller already tracks the mask's popcount (incremental kernels) -- skips a full pass.
+__device__ inline int warp_sample(const uint32_t *mb, int AW, int lane, uint64_t seed, uint32_t env, uint32_t t,
+                                  int known_total = -1) {
+    int total = known_total;
+    if (total < 0) {
+        total = 0;
+        for (int w = lane; w < AW; w += 32) total += __popc(mb[w]);
+        total = __reduce_add_sync(GE_FULL, total);
+    }
     if (total <= 0) return -1;
     uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
     int before = 0, action = -1;

@@ -27,6 +27,11 @@ extern "C" int ge_set_error(int code, const char *fmt, ...);
 namespace {
 
 constexpr u64 KEY_NONE = ~0ull;
+#ifndef GE_INCR_MINB
+#define GE_INCR_MINB 8  // resident blocks per SM the tree step kernel is compiled for: 32 registers => 64 warps/SM.
+                        // The kernel is a chain of ~5 dependent memory rounds per env, i.e. latency-bound: measured
+                        // 0.70 / 0.84 / 0.96 G env-steps/s at cfg3 for 4 / 6 / 8 blocks per SM.
+#endif
 
 __device__ __forceinline__ void mask_set(const ge_batch &d, int b, int e) {
     atomicOr(&d.mask_bits[(size_t)b * d.AW + (e >> 5)], 1u << (e & 31));
@@ -108,7 +113,7 @@ __device__ __forceinline__ void publish(const ge_batch &d, const ge_step_out &ou
 }
 
 template <bool SAMPLED>
-__global__ void __launch_bounds__(GE_WPB * 32) incr_tree_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
+__global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
                                                                    uint64_t seed, uint32_t t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
@@ -116,9 +121,17 @@ __global__ void __launch_bounds__(GE_WPB * 32) incr_tree_step_kernel(ge_batch d,
     const bool mc = d.kind == GE_MULTICAST_ROUTING;
     const int N = d.N;
     const uint32_t nsteps = d.env_steps ? d.env_steps[b] : 0u;
+    int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4);  // [1] = popcount of the mask
+    uint32_t *nb = d.node_bits + (size_t)b * d.NW;
+    const uint32_t *tg = d.target_bits + (size_t)b * d.NW;
+    // tree / target bitsets live in registers (lane w holds word w) when they fit: membership tests of the
+    // row's endpoints become shuffles instead of a dependent round trip to memory
+    const bool regs = d.NW <= 32;
+    const uint32_t nbw = (regs && lane < d.NW) ? nb[lane] : 0u;
+    const uint32_t tgw = (regs && lane < d.NW) ? tg[lane] : 0u;
     int a;
     if (SAMPLED) {
-        a = warp_sample(d.mask_bits + (size_t)b * d.AW, d.AW, lane, seed, (uint32_t)(d.env_id0 + b), t + nsteps);
+        a = warp_sample(d.mask_bits + (size_t)b * d.AW, d.AW, lane, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         if (lane == 0) actions[b] = a;
     } else {
         a = actions[b];
@@ -139,13 +152,11 @@ __global__ void __launch_bounds__(GE_WPB * 32) incr_tree_step_kernel(ge_batch d,
     const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
     const int32_t *col = d.col + (size_t)b * d.MP;
     const float *w32 = d.w32 + (size_t)b * d.MP;
-    uint32_t *nb = d.node_bits + (size_t)b * d.NW;
-    const uint32_t *tg = d.target_bits + (size_t)b * d.NW;
     const int v = col[a];
     const float w = w32[a];
-    int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4);
     const float cost32 = __fadd_rn((float)d.cost[b], w);
-    const bool v_is_target = (tg[v >> 5] >> (v & 31)) & 1u;
+    const uint32_t tgv = regs ? __shfl_sync(GE_FULL, tgw, v >> 5) : tg[v >> 5];
+    const bool v_is_target = (tgv >> (v & 31)) & 1u;
     const int lo = rp[v], hi = rp[v + 1];
     float dv = 0.f;
     bool violated = false;
@@ -168,9 +179,11 @@ __global__ void __launch_bounds__(GE_WPB * 32) incr_tree_step_kernel(ge_batch d,
         u64 *best = reinterpret_cast<u64 *>(d.bestkey) + (size_t)b * N;
         if (lane == 0) { mask_clear(d, b, a); best[v] = KEY_NONE; }         // a IS the best edge of v under parenting >= 3
         lost = 1;
-        for (int e = lo + lane; e < hi; e += 32) {
-            int x = col[e];
-            if (!((nb[x >> 5] >> (x & 31)) & 1u)) {
+        for (int e0 = lo; e0 < hi; e0 += 32) {
+            const int e = e0 + lane;
+            const int x = e < hi ? col[e] : 0;
+            const uint32_t xw = regs ? __shfl_sync(GE_FULL, nbw, x >> 5) : nb[x >> 5];
+            if (e < hi && !((xw >> (x & 31)) & 1u)) {
                 u64 key = ((u64)__float_as_uint(__fadd_rn(dv, w32[e])) << 32) | (uint32_t)e;
                 u64 old = best[x];
                 if (key < old) {                                            // np.argmin: lowest edge index on ties (:179-185)
@@ -182,10 +195,14 @@ __global__ void __launch_bounds__(GE_WPB * 32) incr_tree_step_kernel(ge_batch d,
         }
     } else {
         const int32_t *rev = d.rev + (size_t)b * d.MP;
-        for (int e = lo + lane; e < hi; e += 32) {
-            int x = col[e];
-            if ((nb[x >> 5] >> (x & 31)) & 1u) { mask_clear(d, b, rev[e]); lost++; }   // x->v was valid, is not any more
-            else { mask_set(d, b, e); gained++; }                                         // v->x becomes valid
+        for (int e0 = lo; e0 < hi; e0 += 32) {
+            const int e = e0 + lane;
+            const int x = e < hi ? col[e] : 0;
+            const uint32_t xw = regs ? __shfl_sync(GE_FULL, nbw, x >> 5) : nb[x >> 5];
+            if (e < hi) {
+                if ((xw >> (x & 31)) & 1u) { mask_clear(d, b, rev[e]); lost++; }   // x->v was valid, is not any more
+                else { mask_set(d, b, e); gained++; }                                 // v->x becomes valid
+            }
         }
     }
     gained = __reduce_add_sync(GE_FULL, gained);
