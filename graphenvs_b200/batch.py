@@ -67,6 +67,8 @@ class BatchedGraphEnv:
             T["adj_bits"] = self._adj_store[:B * d.ADJS].view(B, d.ADJS)
             if N <= 64 and self.spec.step_w == "f64":
                 T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
+            elif self.spec.step_w == "f64":
+                T["wsort"] = z((B, d.MP), torch.float64)             # destination-sorted weights: O(1) adj[u, v] by bit rank
         par = int(P.get("parenting", -1))
         if not force_warp:   # derived / state arrays of the incremental-mask kernels (csrc/ge_incr.cu)
             if env_id == "SteinerTree-v0" or (env_id == "MulticastRouting-v0" and par == 2):
@@ -124,7 +126,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
             t = self.t.get(name)

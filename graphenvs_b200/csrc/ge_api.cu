@@ -42,8 +42,11 @@ static bool uses_adj(int kind) {
 namespace {
 
 // SAMPLED: draw the action from the current mask inside the kernel (ge_step_sampled) and publish it.
-template <bool SAMPLED>
-__global__ void __launch_bounds__(GE_WPB * 32) step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
+// MINB = resident blocks per SM the instantiation is compiled for (register cap 64 / 40 / 32).  The kernels
+// are chains of dependent memory rounds, so occupancy buys throughput until spills cost more: measured
+// per kind (TSP best at 8, DensestSubgraph at 6, DistributionCenter -- shared-memory limited -- at 4).
+template <bool SAMPLED, int MINB>
+__global__ void __launch_bounds__(GE_WPB * 32, MINB) step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
                                                          int words_per_warp, uint64_t seed, uint32_t t) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,6 +156,22 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
             int c = col[e];
             atomicOr(&adj[(size_t)u * d.NW + (c >> 5)], 1u << (c & 31));
         }
+    if (d.wsort && d.w64) {  // weights in ascending-destination order per row: O(1) adj[u, v] lookup by bit rank
+        __syncwarp();
+        __threadfence_block();
+        const double *w64 = d.w64 + (size_t)b * d.MP;
+        double *ws = d.wsort + (size_t)b * d.MP;
+        for (int u = 0; u < d.N; ++u) {
+            const int lo = rp[u], hi = rp[u + 1];
+            const uint32_t *row = adj + (size_t)u * d.NW;
+            for (int e = lo + lane; e < hi; e += 32) {
+                const int v = col[e];
+                int rank = __popc(row[v >> 5] & ((1u << (v & 31)) - 1u));
+                for (int w = 0; w < (v >> 5); ++w) rank += __popc(row[w]);
+                ws[lo + rank] = w64[e];
+            }
+        }
+    }
     if (d.wmat && d.w64) {  // dense float64 weights (the reference's self.adj, shortest_path.py:82)
         double *wm = d.wmat + (size_t)b * d.N * d.N;
         const double *w64 = d.w64 + (size_t)b * d.MP;
@@ -508,13 +527,11 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
-    if (sampled) {
-        if ((rc = set_smem(step_kernel<true>, smem))) return rc;
-        step_kernel<true><<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
-    } else {
-        if ((rc = set_smem(step_kernel<false>, smem))) return rc;
-        step_kernel<false><<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, 0, 0);
-    }
+    const int minb = d->kind == GE_TSP ? 8 : d->kind == GE_DENSEST_SUBGRAPH ? 6 : 4;
+    auto kernel = sampled ? (minb == 8 ? step_kernel<true, 8> : minb == 6 ? step_kernel<true, 6> : step_kernel<true, 4>)
+                          : (minb == 8 ? step_kernel<false, 8> : minb == 6 ? step_kernel<false, 6> : step_kernel<false, 4>);
+    if ((rc = set_smem(kernel, smem))) return rc;
+    kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }

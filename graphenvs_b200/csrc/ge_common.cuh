@@ -142,6 +142,24 @@ __device__ inline int find_edge(const int32_t *rp, const int32_t *col, int u, in
     return -1;
 }
 
+// adj[u, v] of the reference's dense float64 matrix (0 when there is no edge) without scanning the CSR
+// row: the rank of v among the set bits of u's adjacency bit-row indexes the destination-sorted weights.
+// Warp-cooperative (lane w counts word w); result is warp-uniform.
+__device__ inline double edge_weight_ranked(const ge_batch &d, int b, const uint32_t *adj, int u, int v, int lane) {
+    const uint32_t *row = adj + (size_t)u * d.NW;
+    const int vw = v >> 5;
+    int rank = 0;
+    bool present = false;
+    for (int w = lane; w <= vw; w += 32) {
+        uint32_t bits = row[w];
+        if (w == vw) { present = (bits >> (v & 31)) & 1u; bits &= (1u << (v & 31)) - 1u; }
+        rank += __popc(bits);
+    }
+    rank = __reduce_add_sync(GE_FULL, rank);
+    if (!__any_sync(GE_FULL, present)) return 0.0;
+    return d.wsort[(size_t)b * d.MP + d.row_ptr[(size_t)b * d.RP + u] + rank];
+}
+
 // Source node of directed edge e (binary search over row_ptr; warp-uniform when e is).
 __device__ inline int edge_src(const int32_t *rp, int N, int e) {
     int lo = 0, hi = N;  // invariant: rp[lo] <= e < rp[hi]

@@ -422,8 +422,9 @@ __device__ inline void step_env(const ge_batch &d, const EnvPtrs &p, Scr &s, int
     int cnt = 0;
     switch (kind) {
     case GE_SHORTEST_PATH: {  // shortest_path.py:111-141
-        int e = find_edge(p.rp, p.col, head, a, lane);
-        double w = e >= 0 ? p.w64[e] : 0.0;
+        double w;
+        if (d.wsort) w = edge_weight_ranked(d, b, p.adj, head, a, lane);
+        else { int e = find_edge(p.rp, p.col, head, a, lane); w = e >= 0 ? p.w64[e] : 0.0; }
         r.reward = -w;
         cost = cost + w;
         if (a == d.dest[b]) { r.done = 1; r.solved = 1; }
@@ -440,8 +441,11 @@ __device__ inline void step_env(const ge_batch &d, const EnvPtrs &p, Scr &s, int
         bool nb = (p.adj[(size_t)head * d.NW + (a >> 5)] >> (a & 31)) & 1u;
         bool vis = tbit(s.vis, a);
         if (d.parenting >= 1 && (!nb || vis)) { r.status = GE_STEP_INVALID; r.has_mask = 0; return; }
-        int e = nb ? find_edge(p.rp, p.col, head, a, lane) : -1;
-        double w = e >= 0 ? p.w64[e] : 0.0;
+        double w = 0.0;
+        if (nb) {
+            if (d.wsort) w = edge_weight_ranked(d, b, p.adj, head, a, lane);
+            else { int e = find_edge(p.rp, p.col, head, a, lane); w = e >= 0 ? p.w64[e] : 0.0; }
+        }
         r.reward = w;
         cost = cost - w;
         r.sol = cost;  // info['solution_cost'] on every step (:163-165)
@@ -473,8 +477,9 @@ __device__ inline void step_env(const ge_batch &d, const EnvPtrs &p, Scr &s, int
         store_node_bits(d, b, lane, s, false);
         break; }
     case GE_TSP: {  // tsp.py:213-258
-        int e = find_edge(p.rp, p.col, head, a, lane);
-        double w = e >= 0 ? p.w64[e] : 0.0;
+        double w;
+        if (d.wsort) w = edge_weight_ranked(d, b, p.adj, head, a, lane);
+        else { int e = find_edge(p.rp, p.col, head, a, lane); w = e >= 0 ? p.w64[e] : 0.0; }
         r.reward = 0.0 - w;
         cost = cost + w;
         if (lane == 0) s.vis[a >> 5] |= 1u << (a & 31);

@@ -98,6 +98,8 @@ typedef struct ge_batch {
     uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived); allocate 16 B of slack */
     int32_t *rev;                 /* [B, MP]   index of the reverse edge (v->u) of every edge (u->v) (derived), or NULL */
     int32_t *esrc;                /* [B, MP]   source node of every edge (derived), or NULL */
+    double *wsort;                /* [B, MP]   w64 permuted so that every row is in ascending destination order (derived), or
+                                              NULL: adj[u, v] = wsort[row_ptr[u] + rank of v in the adjacency bit-row of u] */
     double *wmin;                 /* [B]       smallest edge weight of the instance (derived), or NULL: lets the cutoff
                                               SSSP skip nodes that cannot relax anything within the cutoff */
     double *wmat;                 /* [B, N, N] dense float64 weight matrix = the reference's self.adj (derived by
@@ -151,7 +153,7 @@ int ge_fill_layout(ge_batch *batch);
 /* Bytes of dynamic shared memory one step launch uses (for diagnostics / occupancy reports). */
 int ge_step_smem_bytes(const ge_batch *batch);
 
-/* Fills every DERIVED graph array whose pointer is set: adj_bits, wmat, rev, esrc, wmin. */
+/* Fills every DERIVED graph array whose pointer is set: adj_bits, wmat, wsort, rev, esrc, wmin. */
 int ge_build_adjacency(const ge_batch *batch, void *stream);
 /* what: bit0 heuristics (SSSP / MST where the reference's value is tie-independent),
  *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw),
