@@ -111,6 +111,8 @@ class BatchedGraphEnv:
         T["mask_bits"] = self._io[16 * Bp:].view(torch.int32).view(B, d.AW)
         if byte_mask:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
+        if auto_reset and N <= 64 and self.spec.action_type == "node":
+            T["mask0_bits"] = z((B, d.AW), torch.int32)     # reset-time mask, reused by auto-reset (lane-per-env kernels)
         T["acc"] = z((4, B), torch.float64)                      # component-major: one stream per statistic
         T["traj"] = z((B,), torch.int64)
         self.env_steps = None   # enable_env_clock(): per-env step counts feeding the samplers (CUDA-graph replays)
@@ -128,7 +130,7 @@ class BatchedGraphEnv:
     def _sync_desc(self):
         for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
-                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "acc", "traj"):
+                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
 

@@ -18,6 +18,8 @@
 // on the row-set expansion (profiles/r01_step_kernel_cfg5_multicast_warp_v1.md).
 //
 // One warp per env (a CSR row is 10-20 edges: one warp iteration); MaxIndependentSet one lane per env.
+#include <cstdlib>
+
 #include "ge_common.cuh"
 
 using namespace ge;
@@ -42,35 +44,88 @@ __device__ __forceinline__ void mask_clear(const ge_batch &d, int b, int e) {
     if (d.mask_bytes) d.mask_bytes[(size_t)b * d.AP + e] = 0;
 }
 
-// Warp-wide zero fill of an env's mask (packed + bytes) with 128-bit stores.
+// A GROUP of G lanes (G = 8, 16 or 32, aligned inside its warp) works on one env.  These kernels are chains of
+// dependent memory rounds -- throughput is (envs in flight) / (chain latency) -- and a CSR row here is 10-20
+// edges, so narrower groups keep 2-4x more envs in flight per resident warp at the same lane utilisation.
+template <int G>
+struct Grp {
+    int gl;         // lane inside the group
+    unsigned mask;  // participation mask of the group inside its warp
+    int base;       // first warp lane of the group
+    __device__ __forceinline__ Grp() {
+        const int lane = threadIdx.x & 31;
+        gl = lane & (G - 1);
+        base = lane & ~(G - 1);
+        mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << base);
+    }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> base) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(mask, v); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+// Group version of ge_common.cuh:warp_sample (same draw): r-th set bit of the packed mask, popcount known.
+template <int G>
+__device__ __forceinline__ int group_sample(const Grp<G> &g, const uint32_t *mb, int AW, uint64_t seed, uint32_t env, uint32_t t, int total) {
+    if (total <= 0) return -1;
+    uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
+    int before = 0, action = -1;
+    for (int w0 = 0; w0 < AW; w0 += G) {
+        int w = w0 + g.gl;
+        uint32_t word = w < AW ? mb[w] : 0u;
+        int c = __popc(word), inc = c;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            int x = __shfl_up_sync(g.mask, inc, o, G);
+            if (g.gl >= o) inc += x;
+        }
+        int chunk = g.shfl(inc, G - 1);
+        if ((int)r < before + chunk) {
+            unsigned hit = g.ballot((int)r < before + inc);
+            int src_lane = __ffs(hit) - 1;
+            int excl = before + inc - c;
+            int pos = (g.gl == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
+            pos = g.shfl(pos, src_lane);
+            action = ((w0 + src_lane) << 5) + pos;
+            break;
+        }
+        before += chunk;
+    }
+    return action;
+}
+
+// Group-wide zero fill of an env's mask (packed + bytes) with 128-bit stores.
+template <int G>
 __device__ __forceinline__ void mask_zero(const ge_batch &d, int b, int lane) {
     uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
-    for (int w = lane; w < d.AW; w += 32) mb[w] = 0;
+    for (int w = lane; w < d.AW; w += G) mb[w] = 0;
     if (d.mask_bytes) {
         uint4 *p = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = lane; i < (d.AP >> 4); i += 32) p[i] = z;
+        for (int i = lane; i < (d.AP >> 4); i += G) p[i] = z;
     }
 }
 
 // State init + first mask (tail of reset()) for the tree-growing kinds.  Returns nothing; all lanes.
-__device__ __forceinline__ void incr_reset_tree(const ge_batch &d, int b, int lane) {
+template <int G>
+__device__ __forceinline__ void incr_reset_tree(const ge_batch &d, int b, const Grp<G> &g) {
+    const int lane = g.gl;
     const bool mc = d.kind == GE_MULTICAST_ROUTING;
     const int src = mc ? 0 : d.src[b];
     const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
     const int32_t *col = d.col + (size_t)b * d.MP;
-    for (int w = lane; w < d.NW; w += 32) d.node_bits[(size_t)b * d.NW + w] = (w == (src >> 5)) ? (1u << (src & 31)) : 0u;
-    mask_zero(d, b, lane);
+    for (int w = lane; w < d.NW; w += G) d.node_bits[(size_t)b * d.NW + w] = (w == (src >> 5)) ? (1u << (src & 31)) : 0u;
+    mask_zero<G>(d, b, lane);
     if (mc) {
-        for (int w = lane; w < d.MW; w += 32) d.edge_bits[(size_t)b * d.MW + w] = 0;
-        for (int v = lane; v < d.N; v += 32) d.dist32[(size_t)b * d.N + v] = (v == 0) ? 0.f : -1.f;
+        for (int w = lane; w < d.MW; w += G) d.edge_bits[(size_t)b * d.MW + w] = 0;
+        for (int v = lane; v < d.N; v += G) d.dist32[(size_t)b * d.N + v] = (v == 0) ? 0.f : -1.f;
         if (d.bestkey)
-            for (int v = lane; v < d.N; v += 32) d.bestkey[(size_t)b * d.N + v] = KEY_NONE;
+            for (int v = lane; v < d.N; v += G) d.bestkey[(size_t)b * d.N + v] = KEY_NONE;
     }
-    __syncwarp();
+    g.sync();
     __threadfence_block();
     const int lo = rp[src], hi = rp[src + 1];
-    for (int e = lo + lane; e < hi; e += 32) {  // every edge out of the root is valid (and is the best edge of its head)
+    for (int e = lo + lane; e < hi; e += G) {  // every edge out of the root is valid (and is the best edge of its head)
         mask_set(d, b, e);
         if (mc && d.bestkey) {
             float c = __fadd_rn(0.f, d.w32[(size_t)b * d.MP + e]);
@@ -112,11 +167,12 @@ __device__ __forceinline__ void publish(const ge_batch &d, const ge_step_out &ou
     }
 }
 
-template <bool SAMPLED>
+template <bool SAMPLED, int G>
 __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out,
                                                                    uint64_t seed, uint32_t t) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * GE_WPB + warp;
+    const Grp<G> g;
+    const int lane = g.gl;  // lane inside the env's group
+    const int b = blockIdx.x * (GE_WPB * 32 / G) + (int)threadIdx.x / G;
     if (b >= d.B) return;
     const bool mc = d.kind == GE_MULTICAST_ROUTING;
     const int N = d.N;
@@ -126,12 +182,12 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     const uint32_t *tg = d.target_bits + (size_t)b * d.NW;
     // tree / target bitsets live in registers (lane w holds word w) when they fit: membership tests of the
     // row's endpoints become shuffles instead of a dependent round trip to memory
-    const bool regs = d.NW <= 32;
+    const bool regs = d.NW <= G;
     const uint32_t nbw = (regs && lane < d.NW) ? nb[lane] : 0u;
     const uint32_t tgw = (regs && lane < d.NW) ? tg[lane] : 0u;
     int a;
     if (SAMPLED) {
-        a = warp_sample(d.mask_bits + (size_t)b * d.AW, d.AW, lane, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
+        a = group_sample<G>(g, d.mask_bits + (size_t)b * d.AW, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         if (lane == 0) actions[b] = a;
     } else {
         a = actions[b];
@@ -155,7 +211,7 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     const int v = col[a];
     const float w = w32[a];
     const float cost32 = __fadd_rn((float)d.cost[b], w);
-    const uint32_t tgv = regs ? __shfl_sync(GE_FULL, tgw, v >> 5) : tg[v >> 5];
+    const uint32_t tgv = regs ? g.shfl(tgw, v >> 5) : tg[v >> 5];
     const bool v_is_target = (tgv >> (v & 31)) & 1u;
     const int lo = rp[v], hi = rp[v + 1];
     float dv = 0.f;
@@ -179,10 +235,10 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
         u64 *best = reinterpret_cast<u64 *>(d.bestkey) + (size_t)b * N;
         if (lane == 0) { mask_clear(d, b, a); best[v] = KEY_NONE; }         // a IS the best edge of v under parenting >= 3
         lost = 1;
-        for (int e0 = lo; e0 < hi; e0 += 32) {
+        for (int e0 = lo; e0 < hi; e0 += G) {
             const int e = e0 + lane;
             const int x = e < hi ? col[e] : 0;
-            const uint32_t xw = regs ? __shfl_sync(GE_FULL, nbw, x >> 5) : nb[x >> 5];
+            const uint32_t xw = regs ? g.shfl(nbw, x >> 5) : nb[x >> 5];
             if (e < hi && !((xw >> (x & 31)) & 1u)) {
                 u64 key = ((u64)__float_as_uint(__fadd_rn(dv, w32[e])) << 32) | (uint32_t)e;
                 u64 old = best[x];
@@ -195,21 +251,21 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
         }
     } else {
         const int32_t *rev = d.rev + (size_t)b * d.MP;
-        for (int e0 = lo; e0 < hi; e0 += 32) {
+        for (int e0 = lo; e0 < hi; e0 += G) {
             const int e = e0 + lane;
             const int x = e < hi ? col[e] : 0;
-            const uint32_t xw = regs ? __shfl_sync(GE_FULL, nbw, x >> 5) : nb[x >> 5];
+            const uint32_t xw = regs ? g.shfl(nbw, x >> 5) : nb[x >> 5];
             if (e < hi) {
                 if ((xw >> (x & 31)) & 1u) { mask_clear(d, b, rev[e]); lost++; }   // x->v was valid, is not any more
                 else { mask_set(d, b, e); gained++; }                                 // v->x becomes valid
             }
         }
     }
-    gained = __reduce_add_sync(GE_FULL, gained);
-    lost = __reduce_add_sync(GE_FULL, lost);
+    gained = g.sum(gained);
+    lost = g.sum(lost);
     if (mc && d.parenting >= 3) lost = 1;
     c.y += gained - lost;
-    __syncwarp();
+    g.sync();
     if (lane == 0) {
         nb[v >> 5] |= 1u << (v & 31);
         if (mc) {
@@ -237,18 +293,18 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
         if (r.done) d.done[b] = 1;
     }
     if (r.done && (d.flags & GE_FLAG_AUTO_RESET)) {
-        __syncwarp();
+        g.sync();
         __threadfence_block();
-        incr_reset_tree(d, b, lane);
+        incr_reset_tree<G>(d, b, g);
     }
 }
 
 __global__ void __launch_bounds__(GE_WPB * 32) incr_tree_reset_kernel(ge_batch d, const uint8_t *__restrict__ select) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * GE_WPB + warp;
+    const Grp<32> g;
+    const int b = blockIdx.x * GE_WPB + ((int)threadIdx.x >> 5);
     if (b >= d.B) return;
     if (select && !select[b]) return;
-    incr_reset_tree(d, b, lane);
+    incr_reset_tree<32>(d, b, g);
 }
 
 // ---- MaxIndependentSet, one lane per env (any N): the mask loses bit `a`; episode ends after N picks.
@@ -354,9 +410,17 @@ int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bo
         else incr_mis_step_kernel<false><<<(d->B + 255) / 256, 256, 0, st>>>(*d, actions, *out, seed, t);
         return launched("incr_mis_step_kernel");
     }
-    const int blocks = (d->B + GE_WPB - 1) / GE_WPB;
-    if (sampled) incr_tree_step_kernel<true><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
-    else incr_tree_step_kernel<false><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
+    // lanes per env: wide enough to hold the node bitsets in registers (NW <= G) and a typical row in one pass
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("GE_INCR_G"); forced = e ? atoi(e) : 0; }
+    int G = forced ? forced : (d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32);
+    if (G != 8 && G != 16) G = 32;
+    const int per_block = GE_WPB * 32 / G;
+    const int blocks = (d->B + per_block - 1) / per_block;
+    auto kernel = G == 8 ? (sampled ? incr_tree_step_kernel<true, 8> : incr_tree_step_kernel<false, 8>)
+                : G == 16 ? (sampled ? incr_tree_step_kernel<true, 16> : incr_tree_step_kernel<false, 16>)
+                          : (sampled ? incr_tree_step_kernel<true, 32> : incr_tree_step_kernel<false, 32>);
+    kernel<<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
     return launched("incr_tree_step_kernel");
 }
 

@@ -317,11 +317,15 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
     // scalar state (coalesced SoA streams) while the bulk copy is in flight
     LState s;
     int a = -1, dest = 0, src = 0;
-    u64 oldmask = 0, cs = 0;
+    u64 oldmask = 0, cs = 0, mask0 = 0;
     double acc_r = 0.0, w_edge = 0.0;
     float w_node = 0.f;
     bool was_done = false;
     uint32_t nsteps = 0;
+#ifdef GE_KNOBS
+    if (d.flags & 0x1000u) { if (STAGED) mbar_wait(&bar, 0); if (live && R.row(0) == 0x1234567ull) out.reward[b] = 1.f; return; }
+    if (d.flags & 0x2000u) { return; }   // empty kernel (launch floor)
+#endif
     if (live) {
         if (!SAMPLED) a = actions[b];
         if (d.env_steps) nsteps = d.env_steps[b];
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
         was_done = d.done[b] != 0;
         if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) { dest = d.dest[b]; src = d.src[b]; }
         acc_r = d.acc[2 * (size_t)d.B + b];
+        if (d.mask0_bits && (d.flags & GE_FLAG_AUTO_RESET)) mask0 = load_bits64(d.mask0_bits, b, d.AW);
         if (d.traj) cs = d.traj[b];
         // the one dependent load of the step, issued before waiting for the staged rows
         const bool needs_w = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP;
@@ -446,8 +451,11 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
     }
     if (done && (d.flags & GE_FLAG_AUTO_RESET)) {                               // tail of reset()
         lane_init_state(d, src, s);
-        mask = lane_mask(d, R, s, dest, full);
-        if (kind == GE_TSP && mask == 0) mask = 1ull;                           // tsp.py:154-155
+        if (d.mask0_bits) mask = mask0;                                         // reset-time mask of this instance (ge_reset)
+        else {
+            mask = lane_mask(d, R, s, dest, full);
+            if (kind == GE_TSP && mask == 0) mask = 1ull;                       // tsp.py:154-155
+        }
         lane_store_state(d, b, s, mask, kind == GE_DENSEST_SUBGRAPH);
     } else if (write_state) {
         if (done) d.done[b] = 1;
@@ -473,6 +481,10 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_reset_kernel(ge_batch d, const
     if (d.kind == GE_TSP && mask == 0) mask = 1ull;
     d.done[b] = 0;
     *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = make_int4(0, 0, 0, 0);
+    if (d.mask0_bits) {
+        if (d.AW == 1) d.mask0_bits[b] = (uint32_t)mask;
+        else reinterpret_cast<uint2 *>(d.mask0_bits)[b] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+    }
     lane_store_state(d, b, s, mask, false);
 }
 

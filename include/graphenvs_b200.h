@@ -130,6 +130,8 @@ typedef struct ge_batch {
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
+    uint32_t *mask0_bits;         /* [B, AW]  mask right after reset(), written by ge_reset, or NULL.  It depends only on the
+                                              instance, so auto-reset inside ge_step copies it instead of recomputing it */
     double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
     uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
                                               same recurrence as oracle/graphenvs_oracle.c oenv_rollout */

@@ -10,7 +10,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 frd = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").view(torch.int64)
 sink = torch.zeros((), dtype=torch.int64, device="cuda")
 for name, bits in [("full", 0), ("no_bfs", 0x100), ("no_bfs_no_stage", 0x300), ("no_maskbytes", 0x400), ("no_wmat", 0x800),
-                   ("nothing", 0xf00), ("full2", 0)]:
+                   ("nothing", 0xf00), ("stage_only", 0x1000), ("empty", 0x2200), ("full2", 0)]:
     env = BatchedGraphEnv("LongestPath-v0", B, 50, 200, parenting=2, auto_reset=True)
     env.generate(seed=1); env.reset(); env.enable_env_clock()
     env.desc.flags |= bits
@@ -19,9 +19,8 @@ for name, bits in [("full", 0), ("no_bfs", 0x100), ("no_bfs_no_stage", 0x300), (
     def step(e=None):
         flush.fill_(1); torch.sum(frd, dim=(0,), out=sink)
         if e: e[0].record()
-        env.sample_actions(1, 0)
         if e: e[1].record()
-        env.step_async(env.actions_dev)
+        env.step_sampled(1, 0)
         if e: e[2].record()
     for _ in range(5): step()
     torch.cuda.synchronize()
