@@ -334,6 +334,8 @@ def run_ours(args):
         return np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
 
     h_bits.copy_(env.t["mask_bits"])
+    zero_copy = args.e2e == "zero-copy"
+    mirrored = env.enable_zero_copy(h_bits) if zero_copy else False
     torch.cuda.synchronize()
     Ke = max(3, min(K, args.e2e_steps))
     e2e_s = 0.0
@@ -342,7 +344,10 @@ def run_ours(args):
         flush_l2()
         torch.cuda.synchronize()
         c0 = time.perf_counter()
-        env.step_host(h_act, h_rew, h_flg, h_cost, None, h_bits)
+        if zero_copy:
+            env.step_host_direct(h_act, h_rew, h_flg, h_cost, h_bits)
+        else:
+            env.step_host(h_act, h_rew, h_flg, h_cost, None, h_bits)
         c1 = time.perf_counter()
         if k >= 3:
             e2e_s += c1 - c0
@@ -380,8 +385,11 @@ def run_ours(args):
             "clocks": clocks,
             "gpu_launches": (1 if fused else 2) * K,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "timed": "sum of ge_step_host calls (pinned H2D actions, step kernel, one D2H of reward/flags/"
-                             "solution_cost/packed mask, stream sync); host policy between calls untimed"},
+                    "timed": ("sum of ge_step_host calls, zero-copy: the kernel reads the pinned actions and writes reward/flags/"
+                              "solution_cost%s to pinned host memory over PCIe, stream sync%s; host policy between calls untimed"
+                              % ((" + packed mask", "") if mirrored else ("", "; packed mask by one D2H copy"))) if zero_copy else
+                             ("sum of ge_step_host calls (pinned H2D actions, step kernel, one D2H of reward/flags/"
+                              "solution_cost/packed mask, stream sync); host policy between calls untimed")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "step_kernel", "kernel_ms": kern_ms_mean,
                          "bytes_per_env_step": lib_bytes,
@@ -411,6 +419,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
+    ap.add_argument("--e2e", default="copies", choices=["zero-copy", "copies"],
+                    help="copies: H2D + kernel + one D2H (faster here); zero-copy: kernel reads/writes pinned host memory")
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")
     args = ap.parse_args()

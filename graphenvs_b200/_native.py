@@ -68,7 +68,7 @@ class GeBatch(C.Structure):
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
         ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P), ("bestkey", _P),
-        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("mask0_bits", _P), ("acc", _P), ("traj", _P), ("env_steps", _P),
+        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("mask_mirror", _P), ("mask0_bits", _P), ("acc", _P), ("traj", _P), ("env_steps", _P),
     ]
 
 
@@ -78,7 +78,7 @@ class StepOut(C.Structure):
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
            "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
-           "ge_obs_flat", "ge_step_host", "ge_stats"]
+           "ge_obs_flat", "ge_step_host", "ge_mask_mirror_supported", "ge_stats"]
 
 _lib = None
 
@@ -113,6 +113,7 @@ def lib():
     L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
     L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]
     L.ge_stats.argtypes = [BP, _P, _P]
+    L.ge_mask_mirror_supported.argtypes = [BP]
     if L.ge_abi_version() != 1:
         raise NativeError("ABI version mismatch")
     _lib = L

@@ -345,6 +345,22 @@ class BatchedGraphEnv:
         return (blk, blk[:4 * B].view(torch.float32), blk[4 * Bp:4 * Bp + 4 * B].view(B, 4),
                 blk[8 * Bp:8 * Bp + 8 * B].view(torch.float64), blk[16 * Bp:].view(torch.int32).view(B, AW))
 
+    def enable_zero_copy(self, h_mask_bits):
+        """Mirror every packed-mask write into `h_mask_bits` (pinned host memory, e.g. from host_io()).  Returns
+        False for the incremental-mask kinds, whose mask then comes back with one copy in step_host_direct()."""
+        ok = bool(self.lib.ge_mask_mirror_supported(C.byref(self.desc)))
+        if ok:
+            self._mirror_keep = h_mask_bits
+            self.desc.mask_mirror = h_mask_bits.data_ptr()
+            h_mask_bits.copy_(self.t["mask_bits"])
+        return ok
+
+    def step_host_direct(self, h_actions, h_reward, h_flags, h_cost, h_mask_bits=None):
+        """Zero-copy end-to-end step: the kernel reads the pinned actions and writes reward / flags /
+        solution_cost (/ packed mask) straight into pinned host memory; one launch + one sync."""
+        _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), None, C.byref(self._out), _ptr(h_reward),
+                                            _ptr(h_flags), _ptr(h_cost), None, _ptr(h_mask_bits), self._stream()))
+
     def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None):
         """End-to-end C-ABI call with HOST (pinned) buffers: H2D actions, step, D2H results, sync."""
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev),

@@ -568,10 +568,26 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
     return GE_OK;
 }
 
+int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }
+
 int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                  ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)d->B;
+    if (!d_actions) {  // zero-copy: the kernel reads/writes the pinned host buffers itself
+        if (!h_actions || !h_reward || !h_flags || !h_solution_cost) return fail(GE_ERR_ARG, "zero-copy step needs all host buffers");
+        ge_step_out direct = {h_reward, h_flags, h_solution_cost};
+        int rc0 = ge_step(d, h_actions, &direct, stream);
+        if (rc0) return rc0;
+        if (h_mask_bits && !(d->mask_mirror == h_mask_bits && ge_mask_mirror_supported(d)))
+            GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
+        if (h_mask) {
+            if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+            GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
+        }
+        GE_CUDA_OK(cudaStreamSynchronize(st));
+        return GE_OK;
+    }
     GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
     int rc = ge_step(d, d_actions, out, stream);
     if (rc) return rc;

@@ -111,6 +111,7 @@ __device__ inline int emit_mask(const ge_batch &d, int b, int lane, uint32_t *ms
         msk[w] = m;
         cnt += __popc(m);
         d.mask_bits[(size_t)b * d.AW + w] = m;
+        if (d.mask_mirror) d.mask_mirror[(size_t)b * d.AW + w] = m;
     }
     cnt = __reduce_add_sync(GE_FULL, cnt);
     if (d.mask_bytes) {

@@ -243,6 +243,10 @@ __device__ __forceinline__ void lane_store_state(const ge_batch &d, int b, const
     // mask: packed words + bytes (AP <= 64: up to four 128-bit stores)
     if (d.AW == 1) d.mask_bits[b] = (uint32_t)mask;
     else reinterpret_cast<uint2 *>(d.mask_bits)[b] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+    if (d.mask_mirror) {
+        if (d.AW == 1) d.mask_mirror[b] = (uint32_t)mask;
+        else reinterpret_cast<uint2 *>(d.mask_mirror)[b] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
+    }
 #ifdef GE_KNOBS
     if (d.flags & 0x400u) return;
 #endif

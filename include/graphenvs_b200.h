@@ -130,6 +130,9 @@ typedef struct ge_batch {
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
+    uint32_t *mask_mirror;        /* [B, AW]  optional second destination of every packed-mask write, e.g. PINNED HOST memory
+                                              (zero-copy results, see ge_step_host); honoured by the kernels that rewrite
+                                              the whole mask, not by the incremental ones (ge_mask_mirror_supported) */
     uint32_t *mask0_bits;         /* [B, AW]  mask right after reset(), written by ge_reset, or NULL.  It depends only on the
                                               instance, so auto-reset inside ge_step copies it instead of recomputing it */
     double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
@@ -183,6 +186,11 @@ int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *
  * mask_bits are laid out back to back in that order on the device AND on the host (B even), the
  * results come back in one copy.
  * d_actions / out are device staging buffers owned by the caller. */
+/* ZERO-COPY mode (d_actions == NULL): h_actions / h_reward / h_flags / h_solution_cost must be pinned host
+ * memory (device-accessible under UVA); the step kernel reads the actions from it and writes its results
+ * to it directly over PCIe -- no copy calls, one launch, one stream sync.  The packed mask arrives the same
+ * way when batch->mask_mirror == h_mask_bits and ge_mask_mirror_supported(batch), otherwise by one copy. */
+int ge_mask_mirror_supported(const ge_batch *batch);
 int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                  float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
                  uint32_t *h_mask_bits, void *stream);

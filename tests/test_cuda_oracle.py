@@ -152,3 +152,35 @@ def test_fused_sampled_step_equals_sample_then_step(cfg):
     for name in ("traj", "acc", "mask_bits", "node_bits", "head", "cost"):
         assert torch.equal(a.t[name], b.t[name]), name
     assert torch.equal(a.env_steps, b.env_steps) and int(a.env_steps.min()) == T
+
+
+@pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}), ("TSP-v0", 70, 300, {"parenting": 2}),
+                                 ("SteinerTree-v0", 60, 150, {"n_dests": 5}), ("DistributionCenter-v0", 90, 300, {"parenting": 2})],
+                         ids=lambda c: c[0][:-3])
+def test_zero_copy_host_step_equals_copy_path(cfg):
+    """ge_step_host in zero-copy mode (kernel reads/writes pinned host memory) == the memcpy mode == device step."""
+    env_id, N, E, kw = cfg
+    B, T = 200, 25
+    res = []
+    for mode in ("copies", "zero-copy"):
+        e = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+        e.generate(seed=33)
+        e.reset()
+        blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
+        h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
+        if mode == "zero-copy":
+            e.enable_zero_copy(h_bits)
+        log = []
+        for t in range(T):
+            acts = e.sample_actions(9, t).cpu()
+            h_act.copy_(acts)
+            if mode == "zero-copy":
+                e.step_host_direct(h_act, h_rew, h_flg, h_cost, h_bits)
+            else:
+                e.step_host(h_act, h_rew, h_flg, h_cost, None, h_bits)
+            assert torch.equal(h_bits, e.t["mask_bits"].cpu()), "host mask must equal the device mask after the call"
+            log.append((h_rew.clone(), h_flg.clone(), h_cost.clone(), h_bits.clone()))
+        res.append(log)
+    for (r0, f0, c0, m0), (r1, f1, c1, m1) in zip(*res):
+        assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
+        assert torch.equal(torch.nan_to_num(c0, nan=-7.0), torch.nan_to_num(c1, nan=-7.0))
