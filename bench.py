@@ -370,6 +370,13 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:   # measured DRAM bytes per launch of the step kernel (ncu), when this workload/batch was profiled
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
+            if tr and tr.get("envs") == B:
+                traffic = tr["bytes_per_launch"]
+        except Exception:
+            pass
         achieved = lib_bytes * B / (kern_ms_mean * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -391,7 +398,7 @@ def run_ours(args):
                              ("sum of ge_step_host calls (pinned H2D actions, step kernel, one D2H of reward/flags/"
                               "solution_cost/packed mask, stream sync); host policy between calls untimed")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "step_kernel", "kernel_ms": kern_ms_mean,
+                         "traffic": traffic, "kernel": "step kernel of the workload (lane_step / incr_tree_step / step_kernel)", "kernel_ms": kern_ms_mean,
                          "bytes_per_env_step": lib_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "survey_bytes_per_env_step": survey_bytes,
