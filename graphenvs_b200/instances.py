@@ -86,6 +86,42 @@ def _undirected_edges(adj):
         seen.add(u)
 
 
+def multicast_union_of_paths(adj, weight, src, dests):
+    """MulticastRouting eval heuristic (multicast_routing.py:107-115): total weight of the union of the
+    FIRST-FOUND shortest paths src -> each destination.  The value depends on networkx's tie order, so the
+    search restates nx `_dijkstra_multisource` literally (nx:algorithms/shortest_paths/weighted.py:853-881):
+    heap of (dist, insertion counter, node), neighbours in adjacency insertion order, a predecessor is
+    replaced only by a strictly shorter path; paths are rebuilt from the first predecessor; the edge set and
+    its sum use the same Python set / list operations as the reference."""
+    from heapq import heappop, heappush
+    from itertools import count, islice
+    dist, seen, pred = {}, {src: 0}, {}
+    c = count()
+    fringe = [(0, next(c), src)]
+    while fringe:
+        d_v, _, v = heappop(fringe)
+        if v in dist:
+            continue
+        dist[v] = d_v
+        for u in adj[v]:
+            vu = d_v + weight(v, u)
+            if u in dist:
+                continue
+            if u not in seen or vu < seen[u]:
+                seen[u] = vu
+                heappush(fringe, (vu, next(c), u))
+                pred[u] = v
+    paths = {src: [src]}
+    for v in islice(dist, 1, None):
+        paths[v] = paths[pred[v]] + [v]
+    edges = set()
+    for d in dests:
+        path = paths[d]
+        for u, v in zip(path[:-1], path[1:]):
+            edges.add((u, v))
+    return sum([weight(u, v) for u, v in edges])
+
+
 def generate_instance(env_id, p):
     """Instance of `env_id` with constructor parameters `p` (spec.check_ctor_args), consuming the
     global `random` / `numpy.random` streams exactly like the reference's reset()."""
@@ -149,6 +185,11 @@ def generate_instance(env_id, p):
         ins.src = 0
         ins.dests = rnd.choice(np.arange(1, N), size=p["n_dests"], replace=False).astype(np.int32)  # :95
         ins.u01 = float(rnd.rand())                                 # :103 (max_distance itself needs the SSSP)
+        if p.get("is_eval_env"):                                    # :107-115, tie-order dependent => host restatement
+            wm = {}
+            for (u, v), w in zip(links.tolist(), ins.w64):
+                wm[(u, v)] = w
+            ins.heuristic = float(multicast_union_of_paths(adj, lambda u, v: wm[(u, v)], 0, [int(t) for t in ins.dests]))
     elif env_id == "DistributionCenter-v0":
         ins.w64 = matrix_delay(1, 2, 1.0)                           # distribution_center.py:74-80
         ins.node_cost = rnd.randint(1, 4, size=N) / 1.0             # :82

@@ -91,11 +91,11 @@ class GraphEnv(_Base):
             return -1                                              # densest_subgraph.py:88
         if kind == "MaxIndependentSet-v0" and self.params["weighted"]:
             return -1                                              # max_independent_set.py:66-67
-        if self._heur_on_device:
+        if self._heur_on_device or kind == "MulticastRouting-v0":   # Multicast: host restatement in instances.py
             return float(self.core.t["heuristic"][0].item())
         if not self._warned:
             warnings.warn("%s: the reference's eval heuristic here is tie-order dependent (Kou / Christofides / "
-                          "Ramsey / union of first-found paths) and is not provided; heuristic_solution = nan" % kind)
+                          "Ramsey) and is not provided; heuristic_solution = nan" % kind)
             self._warned = True
         return float("nan")
 

@@ -69,3 +69,29 @@ def test_features_large_vs_oracle():
             oe = cu.oracle_from_instance(env_id, ins, env.params)
             f = oe.features64(weighted_pr=(env_id == "TSP-v0")).astype(np.float32)
             np.testing.assert_allclose(feats[b], f, rtol=1e-5, atol=1e-8, err_msg="%s env %d" % (env_id, b))
+
+
+def test_device_heuristics_match_reference_values_beyond_fixture_sizes():
+    """tests/golden/heuristics.json (oracle/gen_heuristic_golden.py): Dijkstra / MST values of the reference's
+    reset(seed) for N = 60-80, recomputed on the device from the host-regenerated instances."""
+    import json, os, random
+    from graphenvs_b200.instances import generate_instance
+    hs = json.load(open(os.path.join(gu.GOLDEN_DIR, "heuristics.json")))
+    groups = {}
+    for h in hs:
+        if h["env_id"] in ("ShortestPath-v0", "SteinerTree-v0"):
+            groups.setdefault((h["env_id"], json.dumps(h["kwargs"], sort_keys=True)), []).append(h)
+    assert groups
+    for (env_id, kws), lst in groups.items():
+        kw = json.loads(kws)
+        n_nodes, n_edges = kw.pop("n_nodes"), kw.pop("n_edges")
+        env = BatchedGraphEnv(env_id, len(lst), n_nodes, n_edges, **kw)
+        inst = []
+        for h in lst:
+            random.seed(h["seed"]); np.random.seed(h["seed"])
+            inst.append(generate_instance(env_id, env.params))
+        env.load_instances(inst)
+        torch.cuda.synchronize()
+        got = env.t["heuristic"].cpu().numpy()
+        for b, h in enumerate(lst):
+            assert got[b] == pytest.approx(h["heuristic"], rel=1e-9), (env_id, kw, h["seed"])

@@ -60,3 +60,24 @@ def test_ctor_rules():
     assert check_ctor_args("LongestPath-v0", 50, -1, {"parenting": 2})["n_edges"] == 367
     assert check_ctor_args("DensestSubgraph-v0", 10, 20, {"parenting": 1})["n_choices"] == 3
     assert check_ctor_args("DistributionCenter-v0", 500, 4000, {})["target_count"] == 100
+
+
+def _heur_golden():
+    import json
+    import os
+    return json.load(open(os.path.join(gu.GOLDEN_DIR, "heuristics.json")))
+
+
+HG = [h for h in _heur_golden() if h["env_id"] == "MulticastRouting-v0"]
+
+
+@pytest.mark.parametrize("h", HG, ids=["MC-N%d-s%d" % (h["kwargs"]["n_nodes"], h["seed"]) for h in HG])
+def test_multicast_union_of_paths_heuristic_is_bit_identical(h):
+    """multicast_routing.py:107-115 depends on networkx's Dijkstra tie order; the host restatement
+    (instances.multicast_union_of_paths) must give the reference's float64 value exactly."""
+    kw = dict(h["kwargs"])
+    p = check_ctor_args(h["env_id"], kw.pop("n_nodes"), kw.pop("n_edges"), kw)
+    random.seed(h["seed"])
+    np.random.seed(h["seed"])
+    ins = generate_instance(h["env_id"], p)
+    assert ins.heuristic == h["heuristic"]
