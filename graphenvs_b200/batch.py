@@ -111,8 +111,8 @@ class BatchedGraphEnv:
         T["mask_bits"] = self._io[16 * Bp:].view(torch.int32).view(B, d.AW)
         if byte_mask:
             T["mask_bytes"] = z((B, d.AP), torch.uint8)
-        if auto_reset and N <= 64 and self.spec.action_type == "node":
-            T["mask0_bits"] = z((B, d.AW), torch.int32)     # reset-time mask, reused by auto-reset (lane-per-env kernels)
+        if auto_reset and self.spec.action_type == "node":
+            T["mask0_bits"] = z((B, d.AW), torch.int32)     # reset-time mask, reused by auto-reset (lane / group kernels)
         T["acc"] = z((4, B), torch.float64)                      # component-major: one stream per statistic
         T["traj"] = z((B,), torch.int64)
         self.env_steps = None   # enable_env_clock(): per-env step counts feeding the samplers (CUDA-graph replays)

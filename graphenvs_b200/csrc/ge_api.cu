@@ -380,6 +380,10 @@ bool ge_lane_eligible(const ge_batch *d);
 int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_lane_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 int ge_lane_sample(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, cudaStream_t st);
+// group-per-env row-mask kernels for 64 < N <= 1024 (ge_group.cu)
+bool ge_group_eligible(const ge_batch *d);
+int ge_group_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
+int ge_group_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 // incremental-mask kernels (ge_incr.cu)
 bool ge_incr_eligible(const ge_batch *d);
 int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
@@ -507,6 +511,7 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     if (rc) return rc;
     if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
     if (ge_lane_eligible(d)) return ge_lane_reset(d, select, (cudaStream_t)stream);
+    if (ge_group_eligible(d)) return ge_group_reset(d, select, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_reset(d, select, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
@@ -523,6 +528,7 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
     if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
+    if (ge_group_eligible(d)) return ge_group_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;

@@ -44,56 +44,6 @@ __device__ __forceinline__ void mask_clear(const ge_batch &d, int b, int e) {
     if (d.mask_bytes) d.mask_bytes[(size_t)b * d.AP + e] = 0;
 }
 
-// A GROUP of G lanes (G = 8, 16 or 32, aligned inside its warp) works on one env.  These kernels are chains of
-// dependent memory rounds -- throughput is (envs in flight) / (chain latency) -- and a CSR row here is 10-20
-// edges, so narrower groups keep 2-4x more envs in flight per resident warp at the same lane utilisation.
-template <int G>
-struct Grp {
-    int gl;         // lane inside the group
-    unsigned mask;  // participation mask of the group inside its warp
-    int base;       // first warp lane of the group
-    __device__ __forceinline__ Grp() {
-        const int lane = threadIdx.x & 31;
-        gl = lane & (G - 1);
-        base = lane & ~(G - 1);
-        mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << base);
-    }
-    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> base) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)); }
-    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, G); }
-    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(mask, v); }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-};
-
-// Group version of ge_common.cuh:warp_sample (same draw): r-th set bit of the packed mask, popcount known.
-template <int G>
-__device__ __forceinline__ int group_sample(const Grp<G> &g, const uint32_t *mb, int AW, uint64_t seed, uint32_t env, uint32_t t, int total) {
-    if (total <= 0) return -1;
-    uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
-    int before = 0, action = -1;
-    for (int w0 = 0; w0 < AW; w0 += G) {
-        int w = w0 + g.gl;
-        uint32_t word = w < AW ? mb[w] : 0u;
-        int c = __popc(word), inc = c;
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-            int x = __shfl_up_sync(g.mask, inc, o, G);
-            if (g.gl >= o) inc += x;
-        }
-        int chunk = g.shfl(inc, G - 1);
-        if ((int)r < before + chunk) {
-            unsigned hit = g.ballot((int)r < before + inc);
-            int src_lane = __ffs(hit) - 1;
-            int excl = before + inc - c;
-            int pos = (g.gl == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
-            pos = g.shfl(pos, src_lane);
-            action = ((w0 + src_lane) << 5) + pos;
-            break;
-        }
-        before += chunk;
-    }
-    return action;
-}
-
 // Group-wide zero fill of an env's mask (packed + bytes) with 128-bit stores.
 template <int G>
 __device__ __forceinline__ void mask_zero(const ge_batch &d, int b, int lane) {

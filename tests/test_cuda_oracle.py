@@ -17,6 +17,15 @@ pytestmark = pytest.mark.gpu
 CONFIGS = [
     ("ShortestPath-v0", 10, 20, {}, 24),
     ("ShortestPath-v0", 100, 300, {}, 40),
+    ("ShortestPath-v0", 300, 700, {}, 60),                    # group-per-env family, 16 lanes per env
+    ("ShortestPath-v0", 600, 1500, {}, 60),                   # 32 lanes per env
+    ("LongestPath-v0", 100, 300, {"parenting": 1}, 60),
+    ("LongestPath-v0", 80, 200, {"parenting": 0}, 40),
+    ("TSP-v0", 70, 300, {"parenting": 1}, 80),
+    ("TSP-v0", 130, 8385, {"parenting": 1}, 140),            # complete graph
+    ("TSP-v0", 300, 1200, {"parenting": 1}, 100),
+    ("DensestSubgraph-v0", 300, 1500, {"parenting": 1}, 60),
+    ("DensestSubgraph-v0", 600, 3000, {"parenting": 0}, 60),
     ("LongestPath-v0", 50, 200, {"parenting": 2}, 60),       # BASELINE config 2 shape
     ("LongestPath-v0", 33, 70, {"parenting": 2}, 40),
     ("LongestPath-v0", 64, 200, {"parenting": 2}, 60),
