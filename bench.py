@@ -81,7 +81,13 @@ def layout_bytes_per_step(env):
     if k == "ShortestPath-v0":
         graph = nw4 + 8
     elif k in ("LongestPath-v0", "TSP-v0"):
-        graph = (N * nw4 if env.desc.parenting >= 2 else nw4) + (8 if N <= 64 else 8 + deg * 4 + 8)
+        if env.desc.parenting < 2:
+            rows = 2                                       # N(head) for the weight rank, N(a) for the next mask
+        elif N <= 64 or k == "LongestPath-v0":
+            rows = N                                       # the search may touch every row of the bit-matrix
+        else:
+            rows = min(N, 4 + 2 * N / max(deg, 1.0))       # TSP p=2 on N > 64: spanning search + the few internal candidates
+        graph = rows * nw4 + (8 if N <= 64 else 16)
     elif k == "SteinerTree-v0":
         graph = 0.5 * (M * 4 + (N + 1) * 4) + 12 + nw4      # rows of tree nodes: on average half of the CSR
     elif k == "MulticastRouting-v0":

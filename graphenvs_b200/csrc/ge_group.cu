@@ -1,5 +1,6 @@
-// ge_group.cu -- GROUP-PER-ENV kernels for the node-action kinds whose mask is one adjacency row:
-// ShortestPath, LongestPath parenting <= 1, TSP parenting 1, DensestSubgraph, for 64 < N <= 1024.
+// ge_group.cu -- GROUP-PER-ENV kernels for the node-action kinds (ShortestPath, LongestPath, TSP,
+// DensestSubgraph) with 64 < N <= 1024: the mask is one adjacency row, optionally pruned by reachability
+// (LongestPath parenting >= 2) or by cut-vertex tests (TSP parenting 2) on the adjacency bit-matrix.
 //
 // Why: ncu on the general warp-per-env kernel showed these steps ISSUE-bound at ~1,000 warp-instructions
 // per env-step (profiles/r01_step_kernel_cfg4_tsp_p1_warp_v2.md: 60 % issue utilisation, 5 % of HBM peak):
@@ -19,26 +20,114 @@ extern "C" int ge_set_error(int code, const char *fmt, ...);
 namespace {
 
 __host__ __device__ inline bool group_kind(const ge_batch &d) {
-    switch (d.kind) {
-    case GE_SHORTEST_PATH: return true;
-    case GE_LONGEST_PATH: return d.parenting <= 1;
-    case GE_TSP: return d.parenting == 1;
-    case GE_DENSEST_SUBGRAPH: return true;
+    return d.kind == GE_SHORTEST_PATH || d.kind == GE_LONGEST_PATH || d.kind == GE_TSP || d.kind == GE_DENSEST_SUBGRAPH;
+}
+
+constexpr int NO_NODE = 0x7fffffff;
+
+template <int G>
+__device__ __forceinline__ int lowest_node(const Grp<G> &g, uint32_t w) {  // lowest set node id of a distributed set
+    return __reduce_min_sync(g.mask, w ? (g.gl << 5) + __ffs(w) - 1 : NO_NODE);
+}
+
+// Worklist reachability inside `allowed` (one word per lane) from node `seed`; stops once `stop_count` nodes
+// are reached (everything allowed) or the frontier is empty.  Returns the number of reached nodes; leaves
+// the reached set in reach_w and, when `internal` is given, the nodes whose expansion discovered something
+// (the internal nodes of a spanning tree).  Two frontier rows are fetched per trip (independent loads).
+template <int G>
+__device__ __forceinline__ int group_reach(const Grp<G> &g, const uint32_t *adj, int NW, uint32_t allowed, int seed, int stop_count,
+                                           uint32_t &reach_w, uint32_t *internal) {
+    const int lane = g.gl;
+    const bool W = lane < NW;
+    uint32_t reach = (lane == (seed >> 5)) ? (1u << (seed & 31)) : 0u, frontier = reach, inner = 0;
+    int reached = 1;
+    while (reached < stop_count) {
+        const int r1 = lowest_node(g, frontier);
+        if (r1 == NO_NODE) break;
+        if (lane == (r1 >> 5)) frontier &= ~(1u << (r1 & 31));
+        const int r2 = lowest_node(g, frontier);
+        if (r2 != NO_NODE && lane == (r2 >> 5)) frontier &= ~(1u << (r2 & 31));
+        const uint32_t row1 = W ? __ldg(adj + (size_t)r1 * NW + lane) : 0u;
+        const uint32_t row2 = (W && r2 != NO_NODE) ? __ldg(adj + (size_t)r2 * NW + lane) : 0u;
+        uint32_t nx = row1 & allowed & ~reach;
+        int added = g.sum(__popc(nx));
+        if (added && lane == (r1 >> 5)) inner |= 1u << (r1 & 31);
+        reach |= nx; frontier |= nx; reached += added;
+        if (r2 != NO_NODE) {
+            nx = row2 & allowed & ~reach;
+            added = g.sum(__popc(nx));
+            if (added && lane == (r2 >> 5)) inner |= 1u << (r2 & 31);
+            reach |= nx; frontier |= nx; reached += added;
+        }
     }
-    return false;
+    reach_w = reach;
+    if (internal) *internal = inner;
+    return reached;
+}
+
+// LongestPath parenting >= 2 (longest_path.py:133-143): keep the candidates that still reach dest in the
+// graph induced on unvisited nodes (symmetric => one search from dest).
+template <int G>
+__device__ __forceinline__ uint32_t group_prune_longest_path(const ge_batch &d, const Grp<G> &g, const uint32_t *adj, uint32_t m,
+                                                             uint32_t visw, uint32_t tail, int dest) {
+    if ((g.shfl(visw, dest >> 5) >> (dest & 31)) & 1u) return m;                  // dest not in alt_G (:135-136)
+    const uint32_t allowed = ~visw & tail;
+    const int n_alt = g.sum(__popc(allowed));
+    uint32_t reach;
+    group_reach(g, adj, d.NW, allowed, dest, n_alt, reach, nullptr);
+    m &= reach;
+    if (d.parenting == 3 && n_alt <= d.N / 3) m |= allowed;                        // :141-143
+    return m;
+}
+
+// TSP parenting 2 (tsp.py:181-194): drop the candidates whose removal disconnects alt_G = all - start - taken.
+// One spanning search first: only the INTERNAL nodes of a spanning tree can be cut vertices, the literal
+// "remove v, test connectivity" runs for those alone (ascending candidate order like the reference).
+template <int G>
+__device__ __forceinline__ uint32_t group_prune_tsp(const ge_batch &d, const Grp<G> &g, const uint32_t *adj, uint32_t m, uint32_t visw,
+                                                    uint32_t tail) {
+    const int lane = g.gl;
+    uint32_t res = ~visw & tail;
+    if (lane == 0) res &= ~1u;
+    const int n_res = g.sum(__popc(res));
+    uint32_t cand = m;
+    if (n_res >= 2) {
+        uint32_t reach, inner;
+        const int seed = lowest_node(g, res);
+        if (group_reach(g, adj, d.NW, res, seed, n_res, reach, &inner) == n_res) cand &= inner | (lane == 0 ? 1u : 0u);
+    }
+    for (;;) {
+        const int v = lowest_node(g, cand);
+        if (v == NO_NODE) break;
+        if (lane == (v >> 5)) cand &= ~(1u << (v & 31));
+        if (v == 0) continue;
+        if (n_res - 1 == 0) break;                                                 // :191-192
+        uint32_t gw = res;
+        if (lane == (v >> 5)) gw &= ~(1u << (v & 31));
+        uint32_t reach;
+        const int seed = lowest_node(g, gw);
+        if (group_reach(g, adj, d.NW, gw, seed, n_res - 1, reach, nullptr) != n_res - 1 && lane == (v >> 5))
+            m &= ~(1u << (v & 31));                                               // :193-194
+    }
+    return m;
 }
 
 // the lane's word of the mask for the CURRENT state (ge_envs.cuh: mask_head_row / mask_tsp / mask_densest)
 template <int G>
-__device__ __forceinline__ uint32_t group_mask_word(const ge_batch &d, const Grp<G> &g, uint32_t roww, uint32_t visw, uint32_t auxw,
-                                                    uint32_t tail, int k_taken) {
+__device__ __forceinline__ uint32_t group_mask_word(const ge_batch &d, const Grp<G> &g, const uint32_t *adj, int dest, uint32_t roww,
+                                                    uint32_t visw, uint32_t auxw, uint32_t tail, int k_taken) {
     switch (d.kind) {
     case GE_SHORTEST_PATH: return roww & ~visw;                              // shortest_path.py:105-109
-    case GE_LONGEST_PATH: return d.parenting == 0 ? tail : (roww & ~visw);    // longest_path.py:125-132
-    case GE_TSP: {                                                            // tsp.py:174-180 (parenting 1)
+    case GE_LONGEST_PATH: {                                                   // longest_path.py:125-145
+        if (d.parenting == 0) return tail;
+        uint32_t m = roww & ~visw;
+        if (d.parenting >= 2) m = group_prune_longest_path(d, g, adj, m, visw, tail, dest);
+        return m; }
+    case GE_TSP: {                                                            // tsp.py:174-199
         uint32_t m = roww & ~visw;
         int taken = g.sum(__popc(visw));
         if (taken < d.N - 1 && g.gl == 0) m &= ~1u;
+        if (d.parenting >= 2) m = group_prune_tsp(d, g, adj, m, visw, tail);
         return m; }
     case GE_DENSEST_SUBGRAPH:                                                 // densest_subgraph.py:105-129
         if (k_taken == 0) return tail;
@@ -124,7 +213,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
         has_mask = 0; status = GE_STEP_AFTER_DONE;
     } else if (kind == GE_TSP && a == 0 && head == 0) {                          // tsp.py:203-211
         done = 1; reward = -(double)N; solved = 0; sol = -1.0;
-        maskw = group_mask_word(d, g, rowh, visw, auxw, tail, 0);
+        maskw = group_mask_word(d, g, adj, dest, rowh, visw, auxw, tail, 0);
         write_state = true;
     } else if (!(a_ok && ((oldm_a >> (a & 31)) & 1u))) {
         status = GE_STEP_INVALID; has_mask = 0;
@@ -148,7 +237,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
             if (a == dest) { done = 1; solved = 1; }
             if (lane == aw) visw |= abit;
             head = a;
-            maskw = group_mask_word(d, g, rowa, visw, auxw, tail, 0);
+            maskw = group_mask_word(d, g, adj, dest, rowa, visw, auxw, tail, 0);
             if (!done && g.sum(__popc(maskw)) == 0) { done = 1; reward = -(double)N; solved = 0; }
             if (done) sol = cost;
             break; }
@@ -159,7 +248,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
             head = a;
             if (lane == aw) visw |= abit;
             if (a == dest) { done = 1; solved = 1; }
-            maskw = group_mask_word(d, g, rowa, visw, auxw, tail, 0);
+            maskw = group_mask_word(d, g, adj, dest, rowa, visw, auxw, tail, 0);
             if (!done && g.sum(__popc(maskw)) == 0) { done = 1; reward = -2.0 * N; solved = 0; }
             break; }
         case GE_TSP: {                                                            // tsp.py:213-258
@@ -170,6 +259,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
             if (taken == N && a == 0) { done = 1; solved = 1; }
             maskw = rowa & ~visw;
             if (taken < N - 1 && lane == 0) maskw &= ~1u;
+            if (d.parenting >= 2) maskw = group_prune_tsp(d, g, adj, maskw, visw, tail);
             if (!done && g.sum(__popc(maskw)) == 0) { done = 1; reward -= 2.0 * N; solved = 0; }
             if (done) sol = cost;
             break; }
@@ -183,7 +273,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
             c.y += ne; c.x += 1;
             if (lane == aw) visw |= abit;
             cost = (double)c.y / (double)c.x;
-            maskw = group_mask_word(d, g, rowa, visw, auxw, tail, c.x);
+            maskw = group_mask_word(d, g, adj, dest, rowa, visw, auxw, tail, c.x);
             if (c.x == d.n_choices) { done = 1; sol = cost; }
             break; }
         }
@@ -247,7 +337,8 @@ __global__ void __launch_bounds__(256) group_reset_kernel(ge_batch d, const uint
     const int src = seeded ? d.src[b] : 0;
     const uint32_t visw = (seeded && lane == (src >> 5)) ? (1u << (src & 31)) : 0u;
     const uint32_t roww = (W && kind != GE_DENSEST_SUBGRAPH) ? d.adj_bits[(size_t)b * d.ADJS + (size_t)src * NW + lane] : 0u;
-    uint32_t m = group_mask_word(d, g, roww, visw, 0u, tail, 0);
+    const int dest = seeded ? d.dest[b] : 0;
+    uint32_t m = group_mask_word(d, g, d.adj_bits + (size_t)b * d.ADJS, dest, roww, visw, 0u, tail, 0);
     if (kind == GE_TSP && g.sum(__popc(m)) == 0 && lane == 0) m |= 1u;          // tsp.py:154-155
     if (W) {
         d.node_bits[(size_t)b * NW + lane] = visw;

@@ -15,8 +15,8 @@ def has_fast_path(env_id, n_nodes, parenting=None):
     when force_warp=True exercises a different code path worth testing."""
     if n_nodes <= 64 and env_id in LANE_KINDS:
         return True
-    if env_id in ("ShortestPath-v0", "DensestSubgraph-v0") or (env_id in ("LongestPath-v0", "TSP-v0") and parenting in (0, 1)):
-        return True   # group-per-env row-mask kernels (64 < N <= 1024)
+    if env_id in ("ShortestPath-v0", "DensestSubgraph-v0", "LongestPath-v0", "TSP-v0"):
+        return True   # group-per-env kernels (64 < N <= 1024)
     if env_id == "SteinerTree-v0" or env_id == "MaxIndependentSet-v0":
         return True
     return env_id == "MulticastRouting-v0" and (parenting is None or parenting >= 2)
