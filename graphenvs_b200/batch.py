@@ -361,6 +361,20 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), None, C.byref(self._out), _ptr(h_reward),
                                             _ptr(h_flags), _ptr(h_cost), None, _ptr(h_mask_bits), self._stream()))
 
+    def host_stepper(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None, stream=None):
+        """Zero-argument callable = step_host on FIXED pinned buffers, arguments marshalled once.  On a
+        non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
+                _ptr(h_cost), _ptr(h_mask), _ptr(h_mask_bits), C.c_void_p(st.cuda_stream))
+        fn, check = self.lib.ge_step_host, _native.check
+        keep = (h_actions, h_reward, h_flags, h_cost, h_mask, h_mask_bits, st)
+
+        def call():
+            check(fn(*args))
+        call._keep = keep
+        return call
+
     def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None):
         """End-to-end C-ABI call with HOST (pinned) buffers: H2D actions, step, D2H results, sync."""
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev),

@@ -2,6 +2,7 @@
 // See include/graphenvs_b200.h for the ABI and the reference interfaces each call replaces.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ge_envs.cuh"
@@ -576,29 +577,15 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
 
 int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }
 
-int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
-                 ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// The copy-mode body of ge_step_host: H2D actions, step, D2H results (enqueue only, no sync).
+static int step_host_enqueue(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                             ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, cudaStream_t st) {
     const size_t B = (size_t)d->B;
-    if (!d_actions) {  // zero-copy: the kernel reads/writes the pinned host buffers itself
-        if (!h_actions || !h_reward || !h_flags || !h_solution_cost) return fail(GE_ERR_ARG, "zero-copy step needs all host buffers");
-        ge_step_out direct = {h_reward, h_flags, h_solution_cost};
-        int rc0 = ge_step(d, h_actions, &direct, stream);
-        if (rc0) return rc0;
-        if (h_mask_bits && !(d->mask_mirror == h_mask_bits && ge_mask_mirror_supported(d)))
-            GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
-        if (h_mask) {
-            if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
-            GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
-        }
-        GE_CUDA_OK(cudaStreamSynchronize(st));
-        return GE_OK;
-    }
     GE_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-    int rc = ge_step(d, d_actions, out, stream);
+    int rc = ge_step(d, d_actions, out, (void *)st);
     if (rc) return rc;
     // When the caller laid reward | flags | solution_cost | mask_bits out back to back on BOTH sides
-    // (ge_io_bytes / BatchedGraphEnv does), the results come back with ONE copy instead of four.
+    // (BatchedGraphEnv does), the results come back with ONE copy instead of four.
     const char *dr = (const char *)out->reward, *hr = (const char *)h_reward;
     bool packed = h_solution_cost && h_mask_bits && (const char *)out->flags == dr + 4 * B &&
                   (const char *)out->solution_cost == dr + 8 * B && (const char *)d->mask_bits == dr + 16 * B &&
@@ -618,6 +605,83 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
         if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
         GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
     }
+    return GE_OK;
+}
+
+// ge_step_host is a fixed sequence (copy in, one kernel, copy out) over fixed buffers, called once per env
+// step: it is captured into a CUDA graph on first use and replayed with ONE launch call afterwards (three
+// to six driver calls otherwise).  The cache key is the whole descriptor plus every buffer pointer and the
+// stream; anything else re-captures.  Capture is impossible on the legacy default stream: direct path there.
+namespace {
+struct HostStepGraph {
+    ge_batch d;
+    const void *p[10];
+    cudaStream_t st;
+    cudaGraphExec_t exec;
+    bool valid;
+};
+HostStepGraph g_hsg[4];
+int g_hsg_next = 0;
+}  // namespace
+
+int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                 ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)d->B;
+    if (!d_actions) {  // zero-copy: the kernel reads/writes the pinned host buffers itself
+        if (!h_actions || !h_reward || !h_flags || !h_solution_cost) return fail(GE_ERR_ARG, "zero-copy step needs all host buffers");
+        ge_step_out direct = {h_reward, h_flags, h_solution_cost};
+        int rc0 = ge_step(d, h_actions, &direct, stream);
+        if (rc0) return rc0;
+        if (h_mask_bits && !(d->mask_mirror == h_mask_bits && ge_mask_mirror_supported(d)))
+            GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
+        if (h_mask) {
+            if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+            GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
+        }
+        GE_CUDA_OK(cudaStreamSynchronize(st));
+        return GE_OK;
+    }
+    if (!out) return fail(GE_ERR_ARG, "null step buffers");
+    const void *key[10] = {h_actions, d_actions, out->reward, out->flags, out->solution_cost, h_reward, h_flags, h_solution_cost, h_mask,
+                           h_mask_bits};
+    const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && !getenv("GE_NO_HOST_GRAPH");
+    if (capturable) {
+        for (HostStepGraph &g : g_hsg)
+            if (g.valid && g.st == st && memcmp(&g.d, d, sizeof(ge_batch)) == 0 && memcmp(g.p, key, sizeof(key)) == 0) {
+                GE_CUDA_OK(cudaGraphLaunch(g.exec, st));
+                GE_CUDA_OK(cudaStreamSynchronize(st));
+                return GE_OK;
+            }
+        // first call for this (descriptor, buffers, stream): run once directly (also sets kernel attributes), then capture
+        int rc = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
+        if (rc) return rc;
+        GE_CUDA_OK(cudaStreamSynchronize(st));
+        // NOTE: the capture below does not execute anything; the call above already did this step.
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc2 = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc2 == GE_OK && e == cudaSuccess && graph) {
+                HostStepGraph &g = g_hsg[g_hsg_next];
+                g_hsg_next = (g_hsg_next + 1) % 4;
+                if (g.valid) { cudaGraphExecDestroy(g.exec); g.valid = false; }
+                if (cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    memcpy(&g.d, d, sizeof(ge_batch));
+                    memcpy(g.p, key, sizeof(key));
+                    g.st = st;
+                    g.valid = true;
+                }
+            }
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+        } else {
+            (void)cudaGetLastError();
+        }
+        return GE_OK;
+    }
+    int rc = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
+    if (rc) return rc;
     GE_CUDA_OK(cudaStreamSynchronize(st));
     return GE_OK;
 }

@@ -193,3 +193,29 @@ def test_zero_copy_host_step_equals_copy_path(cfg):
     for (r0, f0, c0, m0), (r1, f1, c1, m1) in zip(*res):
         assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
         assert torch.equal(torch.nan_to_num(c0, nan=-7.0), torch.nan_to_num(c1, nan=-7.0))
+
+
+def test_host_stepper_graph_replay_matches_direct_calls():
+    """ge_step_host on a side stream is captured once and replayed as a CUDA graph: identical results to the
+    uncaptured path (default stream) step after step."""
+    B, T = 300, 40
+    logs = []
+    for use_side in (False, True):
+        e = BatchedGraphEnv("LongestPath-v0", B, 50, 200, parenting=2, auto_reset=True)
+        e.generate(seed=41)
+        e.reset()
+        blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
+        h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
+        side = torch.cuda.Stream() if use_side else None
+        torch.cuda.synchronize()
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side)
+        log = []
+        for t in range(T):
+            h_act.copy_(e.sample_actions(3, t).cpu())
+            torch.cuda.synchronize()
+            stepper()
+            assert torch.equal(h_bits, e.t["mask_bits"].cpu())
+            log.append((h_rew.clone(), h_flg.clone(), h_bits.clone()))
+        logs.append(log)
+    for (r0, f0, m0), (r1, f1, m1) in zip(*logs):
+        assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
