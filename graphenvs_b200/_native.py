@@ -27,24 +27,42 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """nvcc -> graphenvs_b200/libgraphenvs_b200.so (sm_100a, -lineinfo)."""
+    """nvcc -> graphenvs_b200/libgraphenvs_b200.so (sm_100a, -lineinfo).  Every .cu is compiled to an object
+    in graphenvs_b200/_build/ (in parallel, only when stale), then linked."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libgraphenvs_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"),
-                                 "-o", LIB_PATH] + _SOURCES
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    if os.environ.get("GE_NVCC_DEFS"):   # e.g. GE_NVCC_DEFS="-DGE_INCR_MINB=6" for tuning experiments
-        cmd[1:1] = os.environ["GE_NVCC_DEFS"].split()
-    if os.environ.get("GE_KNOBS"):   # diagnostic build for profiles/knobs.py
-        cmd.insert(1, "-DGE_KNOBS")
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
+    bdir = os.path.join(_PKG, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    extra = os.environ.get("GE_NVCC_DEFS", "").split()      # e.g. GE_NVCC_DEFS="-DGE_INCR_MINB=6" for tuning experiments
+    if os.environ.get("GE_KNOBS"):                          # diagnostic build for profiles/knobs.py
+        extra.append("-DGE_KNOBS")
+    if verbose:
+        extra.append("-Xptxas=-v")
+    tag = os.path.join(bdir, "flags.txt")
+    flag_sig = " ".join(flags + extra)
+    same_flags = os.path.exists(tag) and open(tag).read() == flag_sig
+    hdr_time = max(os.path.getmtime(p) for p in _HEADERS if os.path.exists(p))
+    jobs, objs = [], []
+    for src in _SOURCES:
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        fresh = (not force and same_flags and os.path.exists(obj)
+                 and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time))
+        if not fresh:
+            cmd = [nvcc] + flags + extra + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"), "-c", src, "-o", obj]
+            jobs.append((src, subprocess.Popen(cmd, env=env)))
+    failed = [src for src, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for %s" % ", ".join(os.path.basename(f) for f in failed))
+    open(tag, "w").write(flag_sig)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs, env=env)
     return LIB_PATH
 
 

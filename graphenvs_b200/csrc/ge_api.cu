@@ -534,9 +534,9 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
-    const int minb = d->kind == GE_TSP ? 8 : d->kind == GE_DENSEST_SUBGRAPH ? 6 : 4;
-    auto kernel = sampled ? (minb == 8 ? step_kernel<true, 8> : minb == 6 ? step_kernel<true, 6> : step_kernel<true, 4>)
-                          : (minb == 8 ? step_kernel<false, 8> : minb == 6 ? step_kernel<false, 6> : step_kernel<false, 4>);
+    // (TSP / DensestSubgraph ran best at 8 / 6 blocks per SM, but they now live in the group family for N <= 1024;
+    //  what is left here -- DistributionCenter, Multicast p=1, N > 1024 -- is shared-memory limited at 4.)
+    auto kernel = sampled ? step_kernel<true, 4> : step_kernel<false, 4>;
     if ((rc = set_smem(kernel, smem))) return rc;
     kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
     GE_CUDA_OK(cudaGetLastError());
