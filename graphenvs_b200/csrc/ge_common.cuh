@@ -352,7 +352,9 @@ __device__ inline void sssp_cutoff_warp(const ge_batch &d, int b, int lane, Scr 
             }
             const int total = __shfl_sync(GE_FULL, incl, 31);
             const int rbase = lo - (incl - len);
-            for (int t0 = 0; t0 < total; t0 += 32) {
+            // Software-pipelined over 32-edge slot groups: the loads of group i+1 (destination + weight) are in
+            // flight while group i is relaxed, so a round costs about one memory latency instead of one per group.
+            auto fetch = [&](int t0, int &v, double &wt, double &dsrc, bool &active) {
                 const int t = t0 + lane;
                 int owner = 0;
 #pragma unroll
@@ -362,10 +364,21 @@ __device__ inline void sssp_cutoff_warp(const ge_batch &d, int b, int lane, Scr 
                 }
                 owner &= 31;
                 const int e = __shfl_sync(GE_FULL, rbase, owner) + t;
-                const double dsrc = __shfl_sync(GE_FULL, du, owner);
-                if (t < total) {
-                    const int v = col[e];
-                    const double nd = dsrc + w64[e];
+                dsrc = __shfl_sync(GE_FULL, du, owner);
+                active = t < total;
+                v = active ? col[e] : 0;
+                wt = active ? w64[e] : 0.0;
+            };
+            int v0 = 0, v1 = 0;
+            double w0 = 0.0, w1 = 0.0, d0 = 0.0, d1 = 0.0;
+            bool a0 = false, a1 = false;
+            if (total > 0) fetch(0, v0, w0, d0, a0);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const bool more = t0 + 32 < total;
+                if (more) fetch(t0 + 32, v1, w1, d1, a1);
+                if (a0) {
+                    const int v = v0;
+                    const double nd = d0 + w0;
                     if (nd <= cutoff) {                                     // nx: skip when dist + w > cutoff
                         const u64 nb = (u64)__double_as_longlong(nd);
                         if (nb < s.q[v]) {
@@ -374,12 +387,16 @@ __device__ inline void sssp_cutoff_warp(const ge_batch &d, int b, int lane, Scr 
                                 if (old == INF) atomicOr(&s.t2[v >> 5], 1u << (v & 31));
                                 if (nd + wmin <= cutoff) {
                                     const uint32_t bit = 1u << (v & 31);
-                                    if (!(atomicOr(&s.t0[v >> 5], bit) & bit)) nxt[atomicAdd(cnt, 1)] = (uint16_t)v;
+                                    if (!(atomicOr(&s.t0[v >> 5], bit) & bit)) {
+                                        nxt[atomicAdd(cnt, 1)] = (uint16_t)v;
+                                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + v));  // next round's row bounds
+                                    }
                                 }
                             }
                         }
                     }
                 }
+                v0 = v1; w0 = w1; d0 = d1; a0 = more && a1;
             }
         }
         __syncwarp();
