@@ -107,53 +107,6 @@ __device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64
     return reach;
 }
 
-// Which of the candidates `cand` are connected to `seed` inside `allowed`?  (LongestPath p>=2:
-// has_path(k, dest) in the residual graph, longest_path.py:137-140.)  Two-sided search: the seed
-// side grows only until every candidate is accounted for, and every still-unknown candidate grows
-// its own component in lock step -- candidates cut off by the visited path sit in tiny fragments
-// that close after a few expansions, so the giant component is never exhausted just to prove a
-// negative.  Mean worklist length at config 2 drops from 21 to 7 rows (30 -> 13 for the slowest
-// lane of a warp), same booleans.
-template <bool STAGED>
-__device__ __forceinline__ u64 connected_candidates(const Rows<STAGED> &R, u64 seed, u64 allowed, u64 cand) {
-    u64 reach = seed, frD = seed;
-    u64 pending = cand & ~reach;
-    while (pending) {
-        const u64 cbit = pending & (~pending + 1ull);
-        u64 comp = cbit, frC = cbit;
-        for (;;) {
-            if (frD) {
-                int r = __ffsll((long long)frD) - 1;
-                frD &= frD - 1;
-                u64 nx = R.row(r) & allowed & ~reach;
-                reach |= nx;
-                frD |= nx;
-                pending &= ~reach;
-                if (!(pending & cbit)) break;            // the seed side reached this candidate
-            }
-            if (frC) {
-                int r = __ffsll((long long)frC) - 1;
-                frC &= frC - 1;
-                u64 nx = R.row(r) & allowed & ~comp;
-                comp |= nx;
-                frC |= nx;
-                if (comp & reach) {                       // touched the seed side: whole fragment is connected
-                    reach |= comp;
-                    frD |= frC;                           // its unexpanded nodes continue on the seed side
-                    pending &= ~reach;
-                    break;
-                }
-            }
-            if (!frC) {                                   // fragment closed without meeting the seed side
-                pending &= ~comp;
-                allowed &= ~comp;
-                break;
-            }
-        }
-    }
-    return cand & reach;
-}
-
 struct LState {
     u64 vis, aux;
     int head, k, ecnt;
