@@ -15,6 +15,8 @@ from typing import Optional
 
 import numpy as np
 
+from . import nx_heuristics
+
 
 @dataclass
 class Instance:
@@ -51,8 +53,9 @@ def _connected(adj, n, skip=-1):
     return cnt == n - (1 if skip >= 0 else 0)
 
 
-def gnm_adjacency(n, m):
-    """nx.gnm_random_graph(n, m) with seed=None: adjacency lists in insertion order."""
+def gnm_adjacency(n, m, edge_order=None):
+    """nx.gnm_random_graph(n, m) with seed=None: adjacency lists in insertion order.  `edge_order`, when given,
+    receives the (u, v) pairs in the order networkx inserted them (enough to rebuild an identical nx.Graph)."""
     adj = [dict() for _ in range(n)]
     if n == 1:
         return adj
@@ -61,6 +64,8 @@ def gnm_adjacency(n, m):
             for v in range(u + 1, n):
                 adj[u][v] = None
                 adj[v][u] = None
+                if edge_order is not None:
+                    edge_order.append((u, v))
         return adj
     nlist = list(range(n))
     cnt = 0
@@ -72,6 +77,8 @@ def gnm_adjacency(n, m):
             continue
         adj[u][v] = None
         adj[v][u] = None
+        if edge_order is not None:
+            edge_order.append((u, v))
         cnt += 1
     return adj
 
@@ -122,6 +129,10 @@ def multicast_union_of_paths(adj, weight, src, dests):
     return sum([weight(u, v) for u, v in edges])
 
 
+def _weight_map(links, w64):
+    return {(int(u), int(v)): float(w) for (u, v), w in zip(links.tolist(), w64)}
+
+
 def generate_instance(env_id, p):
     """Instance of `env_id` with constructor parameters `p` (spec.check_ctor_args), consuming the
     global `random` / `numpy.random` streams exactly like the reference's reset()."""
@@ -129,7 +140,8 @@ def generate_instance(env_id, p):
     weighted = p.get("weighted", True)
     n_graph = N - 1 if env_id == "DensestSubgraph-v0" else N       # densest_subgraph.py:59-65
     while True:
-        adj = gnm_adjacency(n_graph, E)
+        edge_order = []
+        adj = gnm_adjacency(n_graph, E, edge_order)
         if not _connected(adj, n_graph):
             continue
         if env_id == "TSP-v0":                                      # tsp.py:60-71
@@ -162,6 +174,8 @@ def generate_instance(env_id, p):
         ins.w64 = matrix_delay(1, 2, 1.0)                           # steiner_tree.py:62-68
         d = rnd.choice(N, p["n_dests"] + 1, replace=False)          # :73
         ins.src, ins.dests = int(d[0]), d[1:].astype(np.int32)      # :89
+        if p.get("is_eval_env") and 1 < p["n_dests"] < N - 1:       # :84-85 Kou: defined by networkx's iteration order
+            ins.heuristic = nx_heuristics.steiner_kou(N, edge_order, _weight_map(links, ins.w64), d)
     elif env_id == "TSP-v0":
         wmap = {}
         if p.get("spatial"):                                        # tsp.py:79-86
@@ -176,8 +190,12 @@ def generate_instance(env_id, p):
             for u, v in _undirected_edges(adj):
                 wmap[(u, v)] = (rnd.randint(3, 10) / 10.0) if weighted else (rnd.randint(1, 2) / 1.0)
         ins.w64 = np.array([wmap[(u, v)] if (u, v) in wmap else wmap[(v, u)] for u, v in links], dtype=np.float64)
+        if p.get("is_eval_env"):                                    # tsp.py:114-117 Christofides (networkx order)
+            ins.heuristic = nx_heuristics.tsp_christofides(N, edge_order, _weight_map(links, ins.w64))
     elif env_id == "MaxIndependentSet-v0":                          # max_independent_set.py:53-57
         ins.node_cost = (rnd.randint(3, 10, size=N) / 10.0) if weighted else (rnd.randint(1, 2, size=N) / 1.0)
+        if p.get("is_eval_env") and not weighted:                   # max_independent_set.py:62-65 Ramsey (networkx order)
+            ins.heuristic = nx_heuristics.mis_ramsey(N, edge_order)
     elif env_id == "DensestSubgraph-v0":
         pass
     elif env_id == "MulticastRouting-v0":

@@ -91,11 +91,11 @@ class GraphEnv(_Base):
             return -1                                              # densest_subgraph.py:88
         if kind == "MaxIndependentSet-v0" and self.params["weighted"]:
             return -1                                              # max_independent_set.py:66-67
-        if self._heur_on_device or kind == "MulticastRouting-v0":   # Multicast: host restatement in instances.py
-            return float(self.core.t["heuristic"][0].item())
+        if self._heur_on_device or kind == "MulticastRouting-v0" or self.instance.heuristic is not None:
+            return float(self.core.t["heuristic"][0].item())   # device value, or the host value loaded with the instance
         if not self._warned:
-            warnings.warn("%s: the reference's eval heuristic here is tie-order dependent (Kou / Christofides / "
-                          "Ramsey) and is not provided; heuristic_solution = nan" % kind)
+            warnings.warn("%s: the reference's eval heuristic here is defined by networkx's iteration order (Kou / Christofides / "
+                          "Ramsey) and networkx is not importable; heuristic_solution = nan" % kind)
             self._warned = True
         return float("nan")
 

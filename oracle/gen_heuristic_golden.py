@@ -16,6 +16,11 @@ for env_id, kws, seeds in [
                              dict(n_nodes=60, n_edges=300, n_dests=4), dict(n_nodes=120, n_edges=600, n_dests=8),
                              dict(n_nodes=40, n_edges=-1, n_dests=3, weighted=False)], range(8)),
     ("ShortestPath-v0", [dict(n_nodes=80, n_edges=240)], range(4)),
+    ("TSP-v0", [dict(n_nodes=12, n_edges=30, parenting=1), dict(n_nodes=20, n_edges=60, parenting=2),
+                dict(n_nodes=14, n_edges=91, parenting=1), dict(n_nodes=30, n_edges=100, parenting=2, weighted=False)], range(4)),
+    ("MaxIndependentSet-v0", [dict(n_nodes=20, n_edges=40, weighted=False), dict(n_nodes=40, n_edges=120, weighted=False)], range(5)),
+    ("SteinerTree-v0", [dict(n_nodes=30, n_edges=80, n_dests=3), dict(n_nodes=60, n_edges=200, n_dests=5),
+                        dict(n_nodes=40, n_edges=100, n_dests=10, weighted=False)], range(5)),
     ("SteinerTree-v0", [dict(n_nodes=60, n_edges=200, n_dests=59), dict(n_nodes=60, n_edges=200, n_dests=1)], range(4)),
 ]:
     for kw in kws:

@@ -34,9 +34,11 @@ def test_make_reset_step_matches_reference(case):
     Fe = r["edges0"].shape[1]
     np.testing.assert_array_equal(obs[N * F:N * F + M * Fe].reshape(M, Fe), r["edges0"])
     np.testing.assert_array_equal(obs[N * F + M * Fe:].reshape(M, 2), r["edge_links"].astype(np.float32))
+    from graphenvs_b200 import nx_heuristics
     heur_ok = env.core.spec.heuristic_on_device(env.params) or not m["kwargs"].get("is_eval_env") \
-        or env_id in ("DensestSubgraph-v0", "DistributionCenter-v0") \
-        or (env_id == "MaxIndependentSet-v0" and m["kwargs"].get("weighted", True))
+        or env_id in ("DensestSubgraph-v0", "DistributionCenter-v0", "MulticastRouting-v0") \
+        or (env_id == "MaxIndependentSet-v0" and m["kwargs"].get("weighted", True)) \
+        or nx_heuristics.available()       # Kou / Christofides / Ramsey are delegated to networkx when importable
     for t, a in enumerate(r["actions"]):
         obs, reward, done, trunc, info = env.step(int(a))
         assert trunc is False

@@ -81,3 +81,23 @@ def test_multicast_union_of_paths_heuristic_is_bit_identical(h):
     np.random.seed(h["seed"])
     ins = generate_instance(h["env_id"], p)
     assert ins.heuristic == h["heuristic"]
+
+
+HN = [h for h in _heur_golden() if h["env_id"] in ("TSP-v0", "MaxIndependentSet-v0")
+      or (h["env_id"] == "SteinerTree-v0" and 1 < h["kwargs"]["n_dests"] < h["kwargs"]["n_nodes"] - 1)]
+
+
+@pytest.mark.parametrize("h", HN, ids=["%s-N%d-s%d" % (h["env_id"][:-3], h["kwargs"]["n_nodes"], h["seed"]) for h in HN])
+def test_networkx_defined_heuristics_match_reference(h):
+    """Kou / Christofides / Ramsey values are defined by networkx's iteration order; the optional delegate
+    (graphenvs_b200/nx_heuristics.py) rebuilds the reference's nx.Graph insertion order and must return the
+    reference's value (1e-9: only the float summation order of the final edge list may differ)."""
+    pytest.importorskip("networkx")
+    import warnings
+    warnings.filterwarnings("ignore")
+    kw = dict(h["kwargs"])
+    p = check_ctor_args(h["env_id"], kw.pop("n_nodes"), kw.pop("n_edges"), kw)
+    random.seed(h["seed"])
+    np.random.seed(h["seed"])
+    ins = generate_instance(h["env_id"], p)
+    assert ins.heuristic == pytest.approx(h["heuristic"], rel=1e-9, abs=1e-12)
