@@ -19,20 +19,34 @@ class GraphInstance:
         self.nodes, self.edges, self.edge_links = nodes, edges, edge_links
 
 
+def flat_obs_sections(env_id, n_nodes, n_edges):
+    """(start, stop, shape) of the three sections of the flat observation: node matrix, edge matrix, edge list."""
+    node_f, edge_f, _ = get_env_info(env_id)
+    m = 2 * n_edges
+    a = n_nodes * node_f
+    b = a + m * edge_f
+    return (0, a, (n_nodes, node_f)), (a, b, (m, edge_f)), (b, b + 2 * m, (m, 2))
+
+
 def vectorize_graph(graph):
-    return np.concatenate((graph.nodes.flatten(), graph.edges.flatten(), graph.edge_links.flatten()), dtype=np.float32)
+    """GraphInstance -> float32 vector [nodes | edges | edge_links], each row-major (utils.py:87-88)."""
+    parts = (np.asarray(graph.nodes), np.asarray(graph.edges), np.asarray(graph.edge_links))
+    out = np.empty(sum(p.size for p in parts), dtype=np.float32)
+    pos = 0
+    for p in parts:
+        out[pos:pos + p.size] = p.reshape(-1)
+        pos += p.size
+    return out
 
 
 def devectorize_graph(vector, env_id, **kwargs):
-    """vector: [B, L] numpy array or torch tensor (host or device)."""
-    bs = vector.shape[0]
-    node_f, edge_f, _ = get_env_info(env_id)
-    n, m = kwargs["n_nodes"], 2 * kwargs["n_edges"]
-    p1 = n * node_f
-    p2 = p1 + m * edge_f
-    x = vector[:, :p1].reshape(bs, n, node_f)
-    edge_features = vector[:, p1:p2].reshape(bs, m, edge_f)
-    edge_index = vector[:, p2:].reshape(bs, m, 2)
+    """Batched inverse of vectorize_graph (utils.py:14-23).  vector: [B, L] numpy array or torch tensor (host or
+    device); returns (x [B,N,F], edge_features [B,2E,Fe], edge_index [B,2E,2] as int64)."""
+    batch = vector.shape[0]
+    out = []
+    for lo, hi, shape in flat_obs_sections(env_id, kwargs["n_nodes"], kwargs["n_edges"]):
+        out.append(vector[:, lo:hi].reshape((batch,) + shape))
+    x, edge_features, edge_index = out
     edge_index = edge_index.long() if hasattr(edge_index, "long") else edge_index.astype(np.int64)
     return x, edge_features, edge_index
 
