@@ -128,7 +128,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
@@ -237,6 +237,8 @@ class BatchedGraphEnv:
         L, d = self.lib, self.desc
         if self.spec.uses_adj or "rev" in self.t or "esrc" in self.t or "wmin" in self.t:
             _native.check(L.ge_build_adjacency(C.byref(d), self._stream()))
+        if self.env_id == "DistributionCenter-v0" and not (d.flags & 8):
+            self._build_distance_automaton()
         what = 0
         if prepare and self.env_id == "DistributionCenter-v0" and d.parenting == 2:
             what |= PREP_INRANGE
@@ -251,6 +253,54 @@ class BatchedGraphEnv:
         if features:
             _native.check(L.ge_features(C.byref(d), self._stream()))
         self._loaded = True
+
+    def _build_distance_automaton(self):
+        """Exact fp64 distance automaton for the cutoff SSSP (include/graphenvs_b200.h: ge_batch.dfa).  Applies when
+        every edge weight of the batch is one of <= 15 distinct doubles (k/10 in the reference) and the closure of
+        left-fold sums within the cutoff has < 255 values; otherwise the fp64 search stays in charge."""
+        T, d, B, M = self.t, self.desc, self.B, self.M
+        for k in ("wcode", "dfa"):
+            T.pop(k, None)
+        self._sync_desc()
+        w = T.get("w64")
+        if w is None or M == 0:
+            return False
+        ws_t = torch.unique(w[:min(B, 1024), :M])                     # ascending; verified against every edge below
+        if ws_t.numel() == 0 or ws_t.numel() > 15:
+            return False
+        ws = [float(x) for x in ws_t.cpu().numpy()]                    # python floats = IEEE doubles, same adds as DADD
+        cutoff = float(d.max_distance)
+        states, frontier = {0.0}, [0.0]
+        while frontier:
+            s = frontier.pop()
+            for x in ws:
+                t = s + x
+                if t <= cutoff and t not in states:
+                    states.add(t)
+                    frontier.append(t)
+                    if len(states) > 254:
+                        return False
+        st = sorted(states)
+        idx = {v: i for i, v in enumerate(st)}
+        S, W = len(st), len(ws)
+        tab = np.full((S, W), 255, dtype=np.uint8)
+        for i, s in enumerate(st):
+            for j, x in enumerate(ws):
+                if s + x <= cutoff:
+                    tab[i, j] = idx[s + x]
+        expand = np.array([1 if s + ws[0] <= cutoff else 0 for s in st], dtype=np.uint8)
+        code = torch.zeros((B, d.MP), dtype=torch.uint8, device=self.device)
+        step = max(1, (64 << 20) // max(M, 1))
+        for lo in range(0, B, step):
+            seg = w[lo:lo + step, :M]
+            c = torch.searchsorted(ws_t, seg).clamp_(max=W - 1)
+            if not bool((ws_t[c] == seg).all()):
+                return False                                           # a weight outside the sampled set: keep fp64
+            code[lo:lo + step, :M] = c.to(torch.uint8)
+        T["wcode"] = code
+        T["dfa"] = torch.from_numpy(np.concatenate([np.array([S, W], dtype=np.uint8), tab.ravel(), expand])).to(self.device)
+        self._sync_desc()
+        return True
 
     def export_instances(self, env_lo=0, count=None):
         """Host copies of `count` resident instances as `Instance`s (reference edge-order contract)."""

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) prep_inrange_kernel(ge_batch d, i
     const int b = (int)(job / d.n_targets), t = (int)(job % d.n_targets);
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     int node = d.targets[(size_t)b * d.n_targets + t];
-    sssp_cutoff_warp(d, b, lane, s, node, d.max_distance);
+    cutoff_reach(d, b, lane, s, node);
     __syncwarp();
     uint32_t *row = d.in_range + ((size_t)b * d.n_targets + t) * d.NW;
     for (int w = lane; w < d.NW; w += 32) row[w] = s.t2[w];
@@ -536,7 +536,9 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
     // (TSP / DensestSubgraph ran best at 8 / 6 blocks per SM, but they now live in the group family for N <= 1024;
     //  what is left here -- DistributionCenter, Multicast p=1, N > 1024 -- is shared-memory limited at 4.)
-    auto kernel = sampled ? step_kernel<true, 4> : step_kernel<false, 4>;
+    // DistributionCenter on the distance automaton needs half the scratch: 6 blocks per SM fit.
+    const bool six = d->kind == GE_DISTRIBUTION_CENTER && d->wcode && d->dfa && !getenv("GE_DC_MINB4");
+    auto kernel = sampled ? (six ? step_kernel<true, 6> : step_kernel<true, 4>) : (six ? step_kernel<false, 6> : step_kernel<false, 4>);
     if ((rc = set_smem(kernel, smem))) return rc;
     kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
     GE_CUDA_OK(cudaGetLastError());

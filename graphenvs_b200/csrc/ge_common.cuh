@@ -26,8 +26,11 @@ struct Scr {
     uint16_t *lst;  // [2N] two frontier node lists of the cutoff SSSP (DistributionCenter only)
 };
 
+__host__ __device__ inline int dist_words(const ge_batch &d) {  // per-node distance scratch: fp64 bit patterns, or
+    return (d.kind == GE_DISTRIBUTION_CENTER && d.wcode && d.dfa) ? d.N : 2 * d.N;  // 32-bit automaton states
+}
 __host__ __device__ inline int scratch_words(const ge_batch &d) {
-    int w = 2 * d.N + 6 * d.NW + d.AW;
+    int w = ((dist_words(d) + 1) & ~1) + 6 * d.NW + d.AW;
     if (d.kind == GE_DISTRIBUTION_CENTER) w += d.N;  // two uint16 node lists
     return (w + 3) & ~3;  // keep every warp slice 16-byte aligned
 }
@@ -35,7 +38,7 @@ __host__ __device__ inline int scratch_words(const ge_batch &d) {
 __device__ inline Scr carve(uint32_t *base, const ge_batch &d) {
     Scr s;
     s.q = reinterpret_cast<u64 *>(base);
-    uint32_t *p = base + 2 * d.N;
+    uint32_t *p = base + ((dist_words(d) + 1) & ~1);
     s.vis = p; p += d.NW;
     s.aux = p; p += d.NW;
     s.t0 = p; p += d.NW;
@@ -407,6 +410,102 @@ __device__ inline void sssp_cutoff_warp(const ge_batch &d, int b, int lane, Scr 
         uint16_t *tmp = cur; cur = nxt; nxt = tmp;
         __syncwarp();
     }
+}
+
+// The same search on the exact distance AUTOMATON (ge_batch.dfa): when the batch's edge weights come from a
+// small set (k/10 in the reference), every fp64 left-fold sum that stays within the cutoff is one of a few
+// dozen values, enumerated on the host with the same IEEE additions and sorted -- a distance is a state id
+// (order-preserving), dist + w is a table lookup, the 64-bit CAS-spin min becomes a native 32-bit shared
+// atomicMin, and an edge weight is a one-byte code instead of eight bytes.  Bit-identical sets, by
+// construction; tests run both searches against the oracle.
+__device__ inline void sssp_cutoff_dfa(const ge_batch &d, int b, int lane, Scr &s, int source) {
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    const uint8_t *wc = d.wcode + (size_t)b * d.MP;
+    const int W = d.dfa[1];
+    const uint8_t *tab = d.dfa + 2, *expand = tab + (int)d.dfa[0] * W;
+    const int N = d.N;
+    uint32_t *q = reinterpret_cast<uint32_t *>(s.q);
+    uint16_t *cur = s.lst, *nxt = s.lst + N;
+    int *cnt = reinterpret_cast<int *>(s.t1);
+    for (int v = lane; v < N; v += 32) q[v] = 255u;
+    for (int w = lane; w < d.NW; w += 32) { s.t0[w] = 0; s.t2[w] = 0; }
+    __syncwarp();
+    if (lane == 0) { q[source] = 0u; s.t2[source >> 5] = 1u << (source & 31); cur[0] = (uint16_t)source; *cnt = 0; }
+    __syncwarp();
+    int ncur = __ldg(expand) ? 1 : 0;
+    while (ncur > 0) {
+        for (int base0 = 0; base0 < ncur; base0 += 32) {
+            const int i = base0 + lane;
+            int lo = 0, len = 0, du = 0;
+            if (i < ncur) {
+                int u = cur[i];
+                lo = rp[u];
+                len = rp[u + 1] - lo;
+                du = (int)q[u];
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(GE_FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(GE_FULL, incl, 31);
+            const int rbase = lo - (incl - len);
+            auto fetch = [&](int t0, int &v, int &code, int &dsrc, bool &active) {
+                const int t = t0 + lane;
+                int owner = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    int x = __shfl_sync(GE_FULL, incl, owner + step - 1);
+                    if (x <= t) owner += step;
+                }
+                owner &= 31;
+                const int e = __shfl_sync(GE_FULL, rbase, owner) + t;
+                dsrc = __shfl_sync(GE_FULL, du, owner);
+                active = t < total;
+                v = active ? col[e] : 0;
+                code = active ? (int)wc[e] : 0;
+            };
+            int v0 = 0, v1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+            bool a0 = false, a1 = false;
+            if (total > 0) fetch(0, v0, c0, d0, a0);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const bool more = t0 + 32 < total;
+                if (more) fetch(t0 + 32, v1, c1, d1, a1);
+                if (a0) {
+                    const uint32_t nid = __ldg(tab + d0 * W + c0);          // state of fl(dist + w), 255 = beyond the cutoff
+                    if (nid != 255u && nid < q[v0]) {
+                        const uint32_t old = atomicMin(&q[v0], nid);
+                        if (nid < old) {
+                            if (old == 255u) atomicOr(&s.t2[v0 >> 5], 1u << (v0 & 31));
+                            if (__ldg(expand + nid)) {
+                                const uint32_t bit = 1u << (v0 & 31);
+                                if (!(atomicOr(&s.t0[v0 >> 5], bit) & bit)) {
+                                    nxt[atomicAdd(cnt, 1)] = (uint16_t)v0;
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + v0));
+                                }
+                            }
+                        }
+                    }
+                }
+                v0 = v1; c0 = c1; d0 = d1; a0 = more && a1;
+            }
+        }
+        __syncwarp();
+        ncur = *cnt;
+        __syncwarp();
+        if (lane == 0) *cnt = 0;
+        for (int w = lane; w < d.NW; w += 32) s.t0[w] = 0;
+        uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+        __syncwarp();
+    }
+}
+
+// find_nodes_in_range: exact automaton when the batch has one, fp64 search otherwise.  Result set in s.t2.
+__device__ inline void cutoff_reach(const ge_batch &d, int b, int lane, Scr &s, int source) {
+    if (d.wcode && d.dfa) sssp_cutoff_dfa(d, b, lane, s, source);
+    else sssp_cutoff_warp(d, b, lane, s, source, d.max_distance);
 }
 
 // Reachability over the adjacency bit-matrix inside `allowed`, seeded with the bits already in

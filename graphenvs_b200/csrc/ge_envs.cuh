@@ -580,7 +580,7 @@ __device__ inline void step_env(const ge_batch &d, const EnvPtrs &p, Scr &s, int
         float rew = -w;
         if (lane == 0) s.vis[a >> 5] |= 1u << (a & 31);
         __syncwarp();
-        sssp_cutoff_warp(d, b, lane, s, a, d.max_distance);  // find_nodes_in_range (:25-26,155) -> s.t2
+        cutoff_reach(d, b, lane, s, a);  // find_nodes_in_range (:25-26,155) -> s.t2
         int gained = 0;
         for (int wi = lane; wi < d.NW; wi += 32) {
             uint32_t reach = s.t2[wi];

@@ -100,6 +100,13 @@ typedef struct ge_batch {
     int32_t *esrc;                /* [B, MP]   source node of every edge (derived), or NULL */
     double *wsort;                /* [B, MP]   w64 permuted so that every row is in ascending destination order (derived), or
                                               NULL: adj[u, v] = wsort[row_ptr[u] + rank of v in the adjacency bit-row of u] */
+    const uint8_t *wcode;         /* [B, MP]   index of every edge weight in the batch's small set of distinct weights, or NULL */
+    const uint8_t *dfa;           /* exact fp64 distance automaton for the cutoff SSSP, or NULL: [S, W, T[S*W], expand[S]].
+                                              State i = the i-th smallest value reachable as a left-fold fp64 sum of the W
+                                              distinct weights without exceeding max_distance; T[i*W+j] = state of
+                                              fl(value_i + weight_j) or 255 when it exceeds the cutoff; expand[i] = value_i +
+                                              smallest weight <= cutoff.  Built on the host with the same IEEE additions,
+                                              so state order == distance order and every comparison is exact. */
     double *wmin;                 /* [B]       smallest edge weight of the instance (derived), or NULL: lets the cutoff
                                               SSSP skip nodes that cannot relax anything within the cutoff */
     double *wmat;                 /* [B, N, N] dense float64 weight matrix = the reference's self.adj (derived by
