@@ -1,8 +1,11 @@
 // ge_common.cuh -- shared device helpers of the graphenvs_b200 engine (sm_100a).
 //
-// Execution shape: ONE WARP PER ENVIRONMENT.  Every env-level quantity (head, done, reward...)
-// is warp-uniform; node/edge sets are packed bitsets (one 32-bit word per lane where possible),
-// staged in a per-warp slice of dynamic shared memory; warp votes / REDUX do the set algebra.
+// Four kernel families share these helpers:
+//   general   ge_envs.cuh + ge_api.cu   one WARP per env, sets staged in a per-warp shared-memory slice
+//   lane      ge_lane.cu                one LANE per env for N <= 64 (sets are 64-bit registers)
+//   group     ge_group.cu               8/16/32 lanes per env for 64 < N <= 1024 (one set word per lane)
+//   incr      ge_incr.cu                incremental masks for the tree-growing kinds and MaxIndependentSet
+// Node/edge sets are packed bitsets everywhere; warp / group votes and REDUX do the set algebra.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
