@@ -96,7 +96,7 @@ class StepOut(C.Structure):
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
            "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
-           "ge_obs_flat", "ge_step_host", "ge_mask_mirror_supported", "ge_stats"]
+           "ge_obs_flat", "ge_obs_graph", "ge_step_host", "ge_mask_mirror_supported", "ge_stats"]
 
 _lib = None
 
@@ -129,6 +129,7 @@ def lib():
     L.ge_step_sampled.argtypes = [BP, C.c_uint64, C.c_uint32, _P, C.POINTER(StepOut), _P]
     L.ge_obs_len.argtypes = [BP]
     L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
+    L.ge_obs_graph.argtypes = [BP, C.c_int, C.c_int, _P, _P, _P, _P]
     L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]
     L.ge_stats.argtypes = [BP, _P, _P]
     L.ge_mask_mirror_supported.argtypes = [BP]

@@ -452,6 +452,16 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_obs_flat(C.byref(self.desc), int(env_lo), int(count), _ptr(out), self._stream()))
         return out
 
+    def obs_graph(self, env_lo=0, count=None):
+        """(x [count,N,F] f32, edge_features [count,2E,Fe] f32, edge_index [count,2E,2] int64) on the device:
+        utils.devectorize_graph of the flat observation without materialising it (GNN / PyG consumers)."""
+        count = self.B - env_lo if count is None else count
+        x = torch.empty((count, self.N, self.F), dtype=torch.float32, device=self.device)
+        ea = torch.empty((count, self.M, self.Fe), dtype=torch.float32, device=self.device)
+        ei = torch.empty((count, self.M, 2), dtype=torch.int64, device=self.device)
+        _native.check(self.lib.ge_obs_graph(C.byref(self.desc), int(env_lo), int(count), _ptr(x), _ptr(ea), _ptr(ei), self._stream()))
+        return x, ea, ei
+
     def compute_features(self):
         if "features" not in self.t:
             self.t["features"] = torch.zeros((self.B, self.N, 5), dtype=torch.float32, device=self.device)

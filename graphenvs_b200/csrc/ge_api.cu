@@ -185,9 +185,13 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
 }
 
 // Reference wire format (utils.py:87-88): [nodes.ravel | edges.ravel | edge_links.ravel] float32.
-__global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float *__restrict__ out, int L) {
+// GRAPH = true writes the three sections to separate tensors instead -- x float32[count, N, F],
+// edge_attr float32[count, M, Fe], edge_index int64[count, M, 2] -- i.e. what utils.devectorize_graph
+// (utils.py:14-23) would slice out of the flat vector, without the float32 round trip of the indices.
+template <bool GRAPH>
+__global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float *__restrict__ out, int L, float *__restrict__ out_e,
+                                                long long *__restrict__ out_i) {
     const int b = env_lo + blockIdx.x;
-    float *o = out + (size_t)blockIdx.x * L;
     const int N = d.N, M = d.M, kind = d.kind;
     int dyn;
     switch (kind) {
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     default: dyn = 2;
     }
     const int F = dyn + 5, Fe = is_edge_kind(kind) ? 2 : 1;
+    float *o = out + (size_t)blockIdx.x * (GRAPH ? (size_t)N * F : (size_t)L);  // node section (GRAPH) or the whole flat vector
     const uint32_t *vis = d.node_bits + (size_t)b * d.NW;
     const uint32_t *aux = d.node_bits2 ? d.node_bits2 + (size_t)b * d.NW : nullptr;
     const uint32_t *tgt = d.target_bits ? d.target_bits + (size_t)b * d.NW : nullptr;
@@ -247,9 +252,12 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
             }
         } else {
             int j = i - NF - MF, e = j >> 1;
-            val = (j & 1) ? (float)col[e] : (float)edge_src(rp, N, e);
+            int node = (j & 1) ? col[e] : edge_src(rp, N, e);
+            if (GRAPH) { out_i[(size_t)blockIdx.x * 2 * M + j] = node; continue; }
+            val = (float)node;
         }
-        o[i] = val;
+        if (GRAPH && i >= NF) out_e[(size_t)blockIdx.x * MF + (i - NF)] = val;
+        else o[i] = val;
     }
 }
 
@@ -572,7 +580,17 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
-    obs_kernel<<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d));
+    obs_kernel<false><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d), nullptr, nullptr);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_obs_graph(const ge_batch *d, int env_lo, int count, float *x, float *edge_attr, int64_t *edge_index, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
+    if (!x || !edge_attr || !edge_index) return fail(GE_ERR_ARG, "null output buffers");
+    obs_kernel<true><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), edge_attr, (long long *)edge_index);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }

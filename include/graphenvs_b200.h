@@ -18,6 +18,7 @@
  *                      tsp.py:174-258, max_independent_set.py:92-124, densest_subgraph.py:105-196,
  *                      multicast_routing.py:155-266, distribution_center.py:129-174)
  *   ge_obs_flat       utils.vectorize_graph (utils.py:87-88), layout of utils.devectorize_graph
+ *   ge_obs_graph      utils.devectorize_graph (utils.py:14-23) applied on the device: (x, edge_features, edge_index)
  *   ge_features       feature_extraction.generate_features (feature_extraction.py:6-37)
  *   ge_prepare        reset-time derived data: eval heuristics (shortest_path.py:88-90,
  *                     longest_path.py:103-106, steiner_tree.py:77-85), Multicast max_distance
@@ -186,6 +187,9 @@ int ge_step_sampled(const ge_batch *batch, uint64_t seed, uint32_t t, int32_t *a
 /* Reference wire format (utils.py:87-88): out is float32[count, N*F + M*Fe + 2*M]. */
 int ge_obs_len(const ge_batch *batch);
 int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *stream);
+/* The same observation as three tensors (what utils.devectorize_graph, utils.py:14-23, slices out of the flat vector):
+ * x float32[count, N, F], edge_attr float32[count, M, Fe], edge_index int64[count, M, 2] -- no float round trip of indices. */
+int ge_obs_graph(const ge_batch *batch, int env_lo, int count, float *x, float *edge_attr, int64_t *edge_index, void *stream);
 
 /* End-to-end entry with HOST buffers: copies actions H2D, steps, copies reward / flags /
  * solution_cost (and the byte mask [B, AP] when h_mask != NULL, the packed mask [B, AW] when

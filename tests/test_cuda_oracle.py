@@ -224,3 +224,21 @@ def test_host_stepper_graph_replay_matches_direct_calls():
         logs.append(log)
     for (r0, f0, m0), (r1, f1, m1) in zip(*logs):
         assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
+
+
+@pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}), ("MulticastRouting-v0", 60, 200, {"parenting": 4, "n_dests": 3}),
+                                 ("DistributionCenter-v0", 90, 300, {"parenting": 2}), ("TSP-v0", 70, 300, {"parenting": 1})],
+                         ids=lambda c: c[0][:-3])
+def test_obs_graph_equals_devectorized_flat_obs(cfg):
+    """ge_obs_graph == utils.devectorize_graph(ge_obs_flat) (utils.py:14-23), indices as exact int64."""
+    from graphenvs_b200 import utils
+    env_id, N, E, kw = cfg
+    env = BatchedGraphEnv(env_id, 40, N, E, auto_reset=True, structural_features=True, **kw)
+    env.generate(seed=8)
+    env.reset()
+    for t in range(7):
+        env.step_sampled(2, t)
+    flat = env.obs_flat(3, 20)
+    x, ea, ei = env.obs_graph(3, 20)
+    fx, fe, fi = utils.devectorize_graph(flat, env_id, n_nodes=N, n_edges=E)
+    assert torch.equal(x, fx) and torch.equal(ea, fe) and torch.equal(ei, fi) and ei.dtype == torch.int64
