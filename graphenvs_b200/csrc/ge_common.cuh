@@ -62,6 +62,18 @@ __device__ inline uint32_t expand4(uint32_t b) {  // 4 mask bits -> 4 bytes of 0
     return ((b & 0xfu) * 0x00204081u) & 0x01010101u;
 }
 
+// Position of the n-th (0-based) set bit of a word that has more than n bits set: five popcount halvings
+// (the __fns intrinsic is a software loop over the bits).
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const int c = __popc(w & ((1u << s) - 1u));
+        if (n >= c) { n -= c; w >>= s; pos += s; }
+    }
+    return pos;
+}
+
 // Counter-based RNG shared bit-for-bit with oracle/graphenvs_oracle.c (ge_mix).
 __host__ __device__ inline uint32_t mix32(uint64_t seed, uint32_t env, uint32_t t) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)env * 0x100000001ull + (((uint64_t)t) << 32 | 0x5bd1e995u));
@@ -99,7 +111,7 @@ __device__ inline int warp_sample(const uint32_t *mb, int AW, int lane, uint64_t
             unsigned hit = __ballot_sync(GE_FULL, (int)r < before + inc);
             int src_lane = __ffs(hit) - 1;
             int excl = before + inc - c;
-            int pos = (lane == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
+            int pos = (lane == src_lane) ? nth_set_bit(word, (int)r - excl) : 0;
             pos = __shfl_sync(GE_FULL, pos, src_lane);
             action = ((w0 + src_lane) << 5) + pos;
             break;
@@ -149,7 +161,7 @@ __device__ __forceinline__ int group_sample(const Grp<G> &g, const uint32_t *mb,
             unsigned hit = g.ballot((int)r < before + inc);
             int src_lane = __ffs(hit) - 1;
             int excl = before + inc - c;
-            int pos = (g.gl == src_lane) ? (int)__fns(word, 0, (int)r - excl + 1) : 0;
+            int pos = (g.gl == src_lane) ? nth_set_bit(word, (int)r - excl) : 0;
             pos = g.shfl(pos, src_lane);
             action = ((w0 + src_lane) << 5) + pos;
             break;

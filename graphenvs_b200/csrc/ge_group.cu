@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
             const uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t + nsteps) * (uint64_t)total) >> 32);
             const unsigned hit = g.ballot((int)r < inc);
             const int sl = __ffs(hit) - 1;
-            int pos = (lane == sl) ? (int)__fns(oldm, 0, (int)r - (inc - pc) + 1) : 0;
+            int pos = (lane == sl) ? nth_set_bit(oldm, (int)r - (inc - pc)) : 0;
             a = (sl << 5) + g.shfl(pos, sl);
         }
         if (lane == 0) actions[b] = a;

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) incr_mis_step_kernel(ge_batch d, int32_t 
             for (int w = 0; w < d.AW; ++w) {
                 uint32_t word = mb[w];
                 int pc = __popc(word);
-                if ((int)r < pc) { a = (w << 5) + (int)__fns(word, 0, (int)r + 1); break; }
+                if ((int)r < pc) { a = (w << 5) + nth_set_bit(word, (int)r); break; }
                 r -= pc;
             }
         }

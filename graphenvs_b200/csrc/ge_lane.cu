@@ -259,7 +259,7 @@ __device__ __forceinline__ int lane_sample(u64 m, uint64_t seed, uint32_t env, u
     uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
     uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
     int clo = __popc(lo);
-    return (int)r < clo ? (int)__fns(lo, 0, (int)r + 1) : 32 + (int)__fns(hi, 0, (int)r - clo + 1);
+    return (int)r < clo ? nth_set_bit(lo, (int)r) : 32 + nth_set_bit(hi, (int)r - clo);
 }
 
 template <bool STAGED, bool SAMPLED>
