@@ -101,3 +101,28 @@ def test_networkx_defined_heuristics_match_reference(h):
     np.random.seed(h["seed"])
     ins = generate_instance(h["env_id"], p)
     assert ins.heuristic == pytest.approx(h["heuristic"], rel=1e-9, abs=1e-12)
+
+
+def test_gnm_generator_matches_networkx_draw_for_draw():
+    """gnm_adjacency == nx.gnm_random_graph under the same `random` seed: same edges, same adjacency insertion
+    order (the edge-action index of SteinerTree / Multicast is a position in that order), same RNG consumption."""
+    nx = pytest.importorskip("networkx")
+    from graphenvs_b200.instances import gnm_adjacency
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        n = int(rng.integers(2, 60))
+        m = int(rng.integers(0, n * (n - 1) // 2 + 3))
+        seed = int(rng.integers(0, 10_000))
+        random.seed(seed)
+        G = nx.gnm_random_graph(n, m)
+        after_nx = random.random()
+        random.seed(seed)
+        order = []
+        adj = gnm_adjacency(n, m, order)
+        after_mine = random.random()
+        assert after_nx == after_mine, "different number of random draws"
+        assert [list(G.adj[u]) for u in range(n)] == [list(a) for a in adj]
+        H = nx.Graph()
+        H.add_nodes_from(range(n))
+        H.add_edges_from(order)
+        assert [list(H.adj[u]) for u in range(n)] == [list(G.adj[u]) for u in range(n)], "edge order must rebuild G exactly"
