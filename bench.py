@@ -238,62 +238,119 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU side
-def run_ours(args):
+CFG5_TOTAL_ENVS = 524288          # per env kind: 524,288 Multicast + 524,288 DistributionCenter = BASELINE configs[4]'s 1M envs
+_PY_REF = os.path.join(ROOT, "profiles", "r02_python_reference_cpu.json")
+
+
+def python_reference_entry(wl):
+    """The unmodified reference's own gymnasium loop (pure Python + networkx) for this workload, as RECORDED on the build
+    container by oracle/time_python_reference.py (it cannot run on the GPU box: no networkx, no /root/reference)."""
+    try:
+        j = json.load(open(_PY_REF))
+        c = j["configs"][wl]
+        return {"one_core_step_only_steps_per_s": c["one_core"]["step_only_steps_per_s"],
+                "one_core_incl_reset_steps_per_s": c["one_core"]["incl_reset_steps_per_s"],
+                "all_cores_steps_per_s": c["all_cores"]["step_only_steps_per_s"], "cores": c["all_cores"]["processes"],
+                "recorded": j["when"], "host": j["host"], "note": c.get("note"),
+                "source": "profiles/r02_python_reference_cpu.json (oracle/time_python_reference.py); a stated, dated figure, "
+                          "not measured in this run"}
+    except Exception:
+        return None
+
+
+class Dist:
+    """torch.distributed plumbing of the bench: barrier + MAX / SUM over ranks, no-ops at world 1."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class L2Flush:
+    """Between timed steps: a 256 MiB write (evicts the working set; > 126 MB L2) followed by a 256 MiB read (evicts the
+    DIRTY flush lines, so the timed kernel does not pay for their write-back).  Per-step CUDA events exclude it."""
+
+    def __init__(self, torch, dev, mode):
+        self.torch = torch
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.rd = torch.empty(256 << 20, dtype=torch.uint8, device=dev).view(torch.int64) if mode == "write+read" else None
+        self.sink = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1)
+        if self.rd is not None:
+            self.torch.sum(self.rd, dim=(0,), out=self.sink)
+
+
+def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_note=None, sampler=None, seed_env0=None):
+    """One workload on this rank's B envs: device-timed env-steps/s (value), the end-to-end C-ABI number (e2e), the
+    roofline of the step kernel, reset-time costs.  Every rank calls it with the same arguments (barriers inside)."""
     import torch
-    import torch.distributed as dist
     from graphenvs_b200 import BatchedGraphEnv
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = args.workload
-    env_id, N, E, kw, B, survey_bytes, desc = WORKLOADS[wl]
-    if args.envs:
-        B = args.envs
-    K, W = args.steps, args.warmup
-
-    env = BatchedGraphEnv(env_id, B, N, E, device=dev, auto_reset=True, env_id0=rank * B, **kw)
+    env_id, N, E, kw, _, survey_bytes, desc = WORKLOADS[wl]
+    dev, rank, world = D.dev, D.rank, D.world
+    env0 = rank * B if seed_env0 is None else seed_env0
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_build = time.time()
+    env = BatchedGraphEnv(env_id, B, N, E, device=dev, auto_reset=True, env_id0=env0, **kw)
+    g0, g1, g2 = ev(), ev(), ev()
+    g0.record()
     env.generate(seed=SEED)                       # device generator: same distribution as the reference's reset()
+    g1.record()
     env.release_w64()
     env.reset()
+    g2.record()
     torch.cuda.synchronize()
+    t_build = time.time() - t_build
+    reset_block = {"generate_derive_prepare_us_per_env": 1e3 * g0.elapsed_time(g1) / B, "state_reset_us_per_env": 1e3 * g1.elapsed_time(g2) / B,
+                   "host_wall_s": t_build}
     lib_bytes = layout_bytes_per_step(env)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     env.enable_env_clock()      # per-env t for the sampler: captured launches draw fresh actions every replay
     fused = args.mode == "fused"
+    kernel_name = env.step_kernel_name(sampled=fused)
 
-    flush_rd = torch.empty(256 << 20, dtype=torch.uint8, device=dev).view(torch.int64) if args.flush == "write+read" else None
-    sink = torch.zeros((), dtype=torch.int64, device=dev)
-
-    def flush_l2():
-        flush.fill_(1)                        # evicts the working set (write a buffer larger than L2) ...
-        if flush_rd is not None:
-            torch.sum(flush_rd, dim=(0,), out=sink)    # ... then a read pass evicts the DIRTY flush lines, so the timed kernels
-                                              # do not pay for writing the flush buffer back to HBM
-
-    def one_step(ev=None):
-        flush_l2()
-        if ev:
-            ev[0].record()
+    def one_step(evs=None):
+        flush()
+        if evs:
+            evs[0].record()
         if fused:                             # action draw + step in one launch (ge_step_sampled):
             env.step_sampled(SEED, 0)         # the step IS the kernel, no event node in between
         else:
             env.sample_actions(SEED, 0)
-            if ev:
-                ev[1].record()
+            if evs:
+                evs[1].record()
             env.step_async(env.actions_dev)
-        if ev:
-            ev[2].record()
+        if evs:
+            evs[2].record()
 
     for _ in range(W):
         one_step()
     torch.cuda.synchronize()
-    # The step is launch-bound from Python (two ~10-40 us kernels), so the timed steps are replayed from a
+    # The step is launch-bound from Python (one ~10-40 us kernel), so the timed steps are replayed from a
     # CUDA graph of G steps; per-step / per-kernel durations come from external event-record nodes in it.
     G = max(g for g in range(1, min(K, 64) + 1) if K % g == 0)
     launch_mode = "CUDA graph of %d steps replayed %d times, external event nodes around every step" % (G, K // G)
@@ -314,13 +371,10 @@ def run_ours(args):
         def replay():
             for i in range(G):
                 one_step(events[i])
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
         time.sleep(0.25)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    D.barrier()
     w0 = time.time()
     step_ms, kern_ms = [], []
     for _ in range(K // G):
@@ -328,125 +382,253 @@ def run_ours(args):
         torch.cuda.synchronize()
         step_ms += [e[0].elapsed_time(e[2]) for e in events]
         kern_ms += [e[0 if fused else 1].elapsed_time(e[2]) for e in events]
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     w1 = time.time()
-    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    clocks = sampler.stop(w0, w1) if sampler is not None else None
     step_ms, kern_ms = np.array(step_ms), np.array(kern_ms)
     assert step_ms.size == K
-    total_ms = float(step_ms.sum())
-    tt = torch.tensor([total_ms, float(kern_ms.mean())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max, kern_ms_mean = float(tt[0]), float(tt[1])
-    value = world * B * K / (total_ms_max * 1e-3)
+    total_ms_max, kern_ms_mean = D.reduce([float(step_ms.sum()), float(kern_ms.mean())], "max")
+    envs_all = D.reduce([B], "sum")[0]
+    value = envs_all * K / (total_ms_max * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers (ge_step_host), host policy between calls untimed
+    # ---- end to end through the C ABI with host buffers (ge_step_host); the policy between calls is untimed
     d = env.desc
     h_blk, h_rew, h_flg, h_cost, h_bits = env.host_io()
     h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
     rng = np.random.default_rng(SEED + rank)
-
-    def host_mask():
-        return np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
-
     h_bits.copy_(env.t["mask_bits"])
-    zero_copy = args.e2e == "zero-copy"
-    mirrored = env.enable_zero_copy(h_bits) if zero_copy else False
     torch.cuda.synchronize()
     Ke = max(3, min(K, args.e2e_steps))
-    e2e_s = 0.0
     side = torch.cuda.Stream(device=dev)       # a real stream: ge_step_host replays its copy/step/copy sequence as a graph
-    stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side)
+    stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"))
+    e2e_s = 0.0
+    D.barrier()
     for k in range(3 + Ke):
-        h_act.numpy()[:] = host_policy(rng, host_mask())
-        flush_l2()
+        if host_side_policy:               # README loop on the host: uniform valid action from the mask that came back
+            mask = np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
+            h_act.numpy()[:] = host_policy(rng, mask)
+        else:                              # large action spaces (up to 8000 edges x 131072 envs): the same draw on the device, copied out
+            env.sample_actions(SEED, 7)
+            h_act.copy_(env.actions_dev)
+        flush()
         torch.cuda.synchronize()
         c0 = time.perf_counter()
-        if zero_copy:
-            env.step_host_direct(h_act, h_rew, h_flg, h_cost, h_bits)
-        else:
-            stepper()
+        stepper()
         c1 = time.perf_counter()
         if k >= 3:
             e2e_s += c1 - c0
-        assert int(h_flg.numpy()[:, 2].max()) == 0, "host policy produced an invalid action"
-    et = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * Ke / float(et[0])
+        assert int(h_flg.numpy()[:, 2].max()) == 0, "policy produced an invalid action"
+    e2e_s_max = D.reduce([e2e_s], "max")[0]
+    e2e_val = envs_all * Ke / e2e_s_max
     h2d = B * 4
     d2h = B * 16 + B * d.AW * 4
 
-    # ---- episode statistics: the one collective of the path (NCCL all-reduce of 4 doubles)
+    # ---- end to end INCLUDING the observation update for a device-resident consumer: the same host step followed by
+    #      ge_obs_graph of the whole batch's node columns (utils.py:14-23: x [B, N, F]); edge tensors are static / reset-time.
+    e2e_obs = None
+    if args.e2e_obs and hasattr(env, "obs_nodes"):
+        xbuf = torch.empty((B, N, env.F), dtype=torch.float32, device=dev)
+        t_obs = 0.0
+        Ko = max(3, min(Ke, 20))
+        for k in range(2 + Ko):
+            env.sample_actions(SEED, 9)
+            h_act.copy_(env.actions_dev)
+            flush()
+            torch.cuda.synchronize()
+            c0 = time.perf_counter()
+            stepper()
+            env.obs_nodes(out=xbuf)
+            torch.cuda.synchronize()
+            c1 = time.perf_counter()
+            if k >= 2:
+                t_obs += c1 - c0
+        t_obs_max = D.reduce([t_obs], "max")[0]
+        e2e_obs = {"value": envs_all * Ko / t_obs_max, "unit": UNIT, "steps": Ko, "obs_bytes_written_per_env": N * env.F * 4,
+                   "what": "ge_step_host (host actions in, results out) + ge_obs_nodes: x float32[B, N, F] rewritten on the device every step"}
+
     from graphenvs_b200.sharding import reduce_stats
     stats = reduce_stats(env.stats().clone()).cpu().numpy()
+    mem = env.memory_bytes()
+    del env, stepper
+    torch.cuda.empty_cache()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_src = None, None
+    try:   # measured DRAM bytes per launch of the step kernel (ncu), when this workload/batch was profiled
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
+        if tr and tr.get("envs") == B:
+            traffic = tr["bytes_per_launch"]
+            traffic_src = "ncu --set full capture of this kernel at this batch (%s); carried from profiles/traffic.json, not measured in this run" % tr.get("source", "profiles/")
+    except Exception:
+        pass
+    achieved = lib_bytes * B / (kern_ms_mean * 1e-3) / 1e9
+    res = {
+        "name": wl, "workload": desc if envs_total_note is None else envs_total_note,
+        "value": value, "unit": UNIT, "ms_per_step": total_ms_max / K, "steps": K, "envs_per_gpu": B, "envs_total": int(envs_all),
+        "launch": launch_mode, "clocks": clocks,
+        "gpu_launches": (1 if fused else 2) * K,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
+                "timed": ("sum of ge_step_host calls: pinned H2D actions, step kernel, D2H of reward/flags/solution_cost/packed mask, "
+                          "stream sync (%s); policy between calls untimed" % args.e2e)},
+        "e2e_obs": e2e_obs,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
+                     "bytes_per_env_step": lib_bytes,
+                     "bytes_model": "compulsory bytes of this engine's layout and algorithm per env-step (bench.py:layout_bytes_per_step)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "survey_bytes_per_env_step": survey_bytes,
+                     "frac_if_full_recompute_bytes": survey_bytes * B / (kern_ms_mean * 1e-3) / 1e9 / peak,
+                     "frac_if_full_recompute_note": "SURVEY 8(d) bytes of a from-scratch recompute over CSR; NOT this kernel's traffic "
+                                                    "(incremental masks / pruned searches move fewer bytes), may exceed 1"},
+        "reset": reset_block,
+        "wall_ms_per_step_incl_flush": 1e3 * (w1 - w0) / K,
+        "episodes": float(stats[0]), "solved": float(stats[1]),
+        "memory_gb_per_gpu": mem / 1e9,
+    }
+    return res
+
+
+def compact(res):
+    """Entry of the `workloads` array: the figures VERDICT r01 asked the driver-run line to carry per workload."""
+    keep = ("name", "workload", "value", "unit", "ms_per_step", "steps", "envs_per_gpu", "e2e", "e2e_obs", "reset", "cpu_baseline",
+            "cpu_reference_python", "episodes")
+    out = {k: res.get(k) for k in keep if k in res}
+    r = res["roofline"]
+    out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_ms", "bytes_per_env_step")}
+    out["e2e"] = {k: res["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "policy")}
+    return out
+
+
+def feature_costs(D):
+    """feature_extraction.generate_features on the device (ge_features) at the configs that produce structural features
+    at reset (BASELINE configs[3]) and at config 5's graph size: us per env, CUDA events."""
+    import torch
+    from graphenvs_b200 import BatchedGraphEnv
+    out = {}
+    for wl, B in (("cfg4_tsp_p1", 2048), ("cfg4_mis", 2048), ("cfg5_multicast", 2048), ("cfg2_longest_path", 16384)):
+        env_id, N, E, kw, _, _, _ = WORKLOADS[wl]
+        env = BatchedGraphEnv(env_id, B, N, E, device=D.dev, structural_features=True, **kw)
+        env.generate(seed=SEED)       # includes one ge_features pass (warm-up)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        env.compute_features()
+        b.record()
+        torch.cuda.synchronize()
+        out[wl] = {"envs": B, "n_nodes": N, "n_edges": E, "us_per_env": 1e3 * a.elapsed_time(b) / B}
+        del env
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    D = Dist()
+    rank, world = D.rank, D.world
+    wl = args.workload
+    env_id, N, E, kw, B, survey_bytes, desc = WORKLOADS[wl]
+    if args.envs:
+        B = args.envs
+    K, W = args.steps, args.warmup
+    flush = L2Flush(torch, D.dev, args.flush)
+    sampler = ClockSampler(D.local) if rank == 0 else None
+    t_all = time.time()
+    head = measure_workload(D, flush, wl, B, K, W, args, host_side_policy=True, sampler=sampler)
+    if world == 1 and not args.no_cpu:
+        head["cpu_baseline"] = cpu_rate(wl, args.cpu_seconds)
+    head["cpu_reference_python"] = python_reference_entry(wl)
+
+    # ---- every other workload of BASELINE.json (one GPU): same protocol, fewer steps, short CPU sample
+    workloads = [compact(head)]
+    if world == 1 and not args.only_headline and not args.envs:
+        for name in WORKLOADS:
+            if name == wl:
+                continue
+            Kw = min(max(K, 100), CAPS.get(name, 1000))
+            r = measure_workload(D, flush, name, WORKLOADS[name][4], Kw, 3, args, host_side_policy=(WORKLOADS[name][1] <= 64))
+            if not args.no_cpu:
+                r["cpu_baseline"] = cpu_rate(name, args.cpu_seconds_other)
+            r["cpu_reference_python"] = python_reference_entry(name)
+            workloads.append(compact(r))
+
+    # ---- BASELINE configs[4] as stated: 1M envs in total (524,288 Multicast + 524,288 DistributionCenter) sharded
+    #      over the ranks -- STRONG scaling: each rank owns total/world envs of each kind, no data-path collective.
+    cfg5 = None
+    if not args.only_headline and not args.envs and not args.no_cfg5:
+        from graphenvs_b200.sharding import rank_slice
+        cfg5 = {"scaling": "strong", "envs_total_per_kind": CFG5_TOTAL_ENVS, "n_gpus": world}
+        tot_ms = 0.0
+        for name in ("cfg5_multicast", "cfg5_distcenter"):
+            lo, cnt = rank_slice(CFG5_TOTAL_ENVS, rank, world)
+            r = measure_workload(D, flush, name, cnt, args.cfg5_steps, 3, args, host_side_policy=False, seed_env0=lo,
+                                 envs_total_note="%s, %d envs in total sharded over %d GPU(s)" % (WORKLOADS[name][6].split(",")[0], CFG5_TOTAL_ENVS, world))
+            cfg5[name] = compact(r)
+            cfg5[name]["memory_gb_per_gpu"] = r["memory_gb_per_gpu"]
+            tot_ms += r["ms_per_step"]
+        cfg5["combined"] = {"value": 2 * CFG5_TOTAL_ENVS / (tot_ms * 1e-3), "unit": UNIT, "ms_per_step_pair": tot_ms,
+                            "what": "one step of all 1,048,576 envs = the Multicast launch + the DistributionCenter launch, back to back"}
+
+    feats = feature_costs(D) if (world == 1 and not args.only_headline and not args.envs) else None
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        try:   # measured DRAM bytes per launch of the step kernel (ncu), when this workload/batch was profiled
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
-            if tr and tr.get("envs") == B:
-                traffic = tr["bytes_per_launch"]
-        except Exception:
-            pass
-        achieved = lib_bytes * B / (kern_ms_mean * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64/f32 + bitsets", "data": "synthetic",
             "config": {"workload": desc, "name": wl, "envs_per_gpu": B, "envs_total": B * world,
                        "instances": "device generator ge_generate (connected G(n,m), reference weight law), seed %d" % SEED,
                        "policy": "uniform valid action, device counter RNG, inside the timed step (%s)" %
-                                 ("drawn in the step kernel, ge_step_sampled" if fused else "ge_sample_actions + ge_step"),
+                                 ("drawn in the step kernel, ge_step_sampled" if args.mode == "fused" else "ge_sample_actions + ge_step"),
                        "auto_reset": True, "l2": "256 MiB flush %s between timed steps (per-step CUDA events exclude it)" % args.flush,
-                       "launch": launch_mode,
-                       "byte_mask": True},
-            "clocks": clocks,
-            "gpu_launches": (1 if fused else 2) * K,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "timed": ("sum of ge_step_host calls, zero-copy: the kernel reads the pinned actions and writes reward/flags/"
-                              "solution_cost%s to pinned host memory over PCIe, stream sync%s; host policy between calls untimed"
-                              % ((" + packed mask", "") if mirrored else ("", "; packed mask by one D2H copy"))) if zero_copy else
-                             ("sum of ge_step_host calls (pinned H2D actions, step kernel, one D2H of reward/flags/"
-                              "solution_cost/packed mask, stream sync); host policy between calls untimed")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step kernel of the workload (lane_step / incr_tree_step / step_kernel)", "kernel_ms": kern_ms_mean,
-                         "bytes_per_env_step": lib_bytes,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "survey_bytes_per_env_step": survey_bytes,
-                         "frac_survey_bytes": survey_bytes * B / (kern_ms_mean * 1e-3) / 1e9 / peak},
-            "wall_ms_per_step_incl_flush": 1e3 * (w1 - w0) / K,
-            "episodes": float(stats[0]), "solved": float(stats[1]),
-            "memory_gb_per_gpu": env.memory_bytes() / 1e9,
+                       "launch": head["launch"], "byte_mask": True},
+            "clocks": head["clocks"],
+            "gpu_launches": head["gpu_launches"],
+            "e2e": head["e2e"], "e2e_obs": head["e2e_obs"],
+            "roofline": head["roofline"],
+            "reset": head["reset"],
+            "wall_ms_per_step_incl_flush": head["wall_ms_per_step_incl_flush"],
+            "episodes": head["episodes"], "solved": head["solved"], "memory_gb_per_gpu": head["memory_gb_per_gpu"],
+            "cpu_reference_python": head["cpu_reference_python"],
+            "workloads": workloads,
+            "cfg5_strong_scaling": cfg5,
+            "feature_extraction_us_per_env": feats,
+            "bench_wall_s": time.time() - t_all,
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_rate(wl, args.cpu_seconds)
+        if "cpu_baseline" in head:
+            line["cpu_baseline"] = head["cpu_baseline"]
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
+
+
+# per-workload cap on timed steps in the all-workloads pass (keeps the default run within minutes)
+CAPS = {"cfg5_distcenter": 200, "cfg5_multicast": 400, "cfg4_tsp_p2": 400}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU (headline only)")
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds-other", type=float, default=3.0, help="CPU sample per workload in the all-workloads pass")
+    ap.add_argument("--cfg5-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the all-workloads pass, config 5 and the feature costs")
+    ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--no-e2e-obs", dest="e2e_obs", action="store_false")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
-    ap.add_argument("--e2e", default="copies", choices=["zero-copy", "copies"],
-                    help="copies: H2D + kernel + one D2H (faster here); zero-copy: kernel reads/writes pinned host memory")
+    ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],
+                    help="pipelined: ge_step_host in chunks on two streams (copies overlap kernels); single: one copy-in / kernel / copy-out")
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")
     args = ap.parse_args()

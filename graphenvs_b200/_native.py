@@ -80,7 +80,7 @@ class GeBatch(C.Structure):
         ("parenting", C.c_int32), ("n_dests", C.c_int32), ("n_choices", C.c_int32), ("n_targets", C.c_int32),
         ("flags", C.c_uint32), ("env_id0", C.c_int32),
         ("NW", C.c_int32), ("MW", C.c_int32), ("A", C.c_int32), ("AW", C.c_int32), ("AP", C.c_int32),
-        ("RP", C.c_int32), ("MP", C.c_int32), ("ADJS", C.c_int32),
+        ("RP", C.c_int32), ("MP", C.c_int32), ("ADJS", C.c_int32), ("acc_stride", C.c_int32), ("reserved0", C.c_int32),
         ("max_distance", C.c_double),
         ("row_ptr", _P), ("col", _P), ("w32", _P), ("w64", _P), ("adj_bits", _P), ("rev", _P), ("esrc", _P), ("wsort", _P), ("wcode", _P), ("dfa", _P), ("wmin", _P), ("wmat", _P),
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
@@ -95,8 +95,9 @@ class StepOut(C.Structure):
 
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
-           "ge_prepare", "ge_features", "ge_generate", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
-           "ge_obs_flat", "ge_obs_graph", "ge_step_host", "ge_mask_mirror_supported", "ge_stats"]
+           "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
+           "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined",
+           "ge_step_host_release", "ge_mask_mirror_supported", "ge_stats"]
 
 _lib = None
 
@@ -123,6 +124,7 @@ def lib():
     L.ge_prepare.argtypes = [BP, C.c_int, _P, _P]
     L.ge_features.argtypes = [BP, _P]
     L.ge_generate.argtypes = [BP, C.c_uint64, _P, _P, _P, _P, _P]
+    L.ge_generate_fallbacks.argtypes = [_P]
     L.ge_reset.argtypes = [BP, _P, _P]
     L.ge_step.argtypes = [BP, _P, C.POINTER(StepOut), _P]
     L.ge_sample_actions.argtypes = [BP, C.c_uint64, C.c_uint32, _P, _P]
@@ -131,9 +133,15 @@ def lib():
     L.ge_obs_flat.argtypes = [BP, C.c_int, C.c_int, _P, _P]
     L.ge_obs_graph.argtypes = [BP, C.c_int, C.c_int, _P, _P, _P, _P]
     L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]
+    L.ge_step_host_pipelined.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, C.c_int, _P]
+    L.ge_step_host_release.argtypes = [BP]
+    L.ge_obs_nodes.argtypes = [BP, C.c_int, C.c_int, _P, _P]
+    L.ge_step_kernel_name.argtypes = [BP, C.c_int]
+    L.ge_step_kernel_name.restype = C.c_char_p
+    L.ge_batch_slice.argtypes = [BP, C.c_int, C.c_int, BP]
     L.ge_stats.argtypes = [BP, _P, _P]
     L.ge_mask_mirror_supported.argtypes = [BP]
-    if L.ge_abi_version() != 1:
+    if L.ge_abi_version() != 2:
         raise NativeError("ABI version mismatch")
     _lib = L
     return L

@@ -63,8 +63,9 @@ class BatchedGraphEnv:
         if self.spec.step_w == "f64" or (keep_w64 and self.spec.step_w == "f32"):
             T["w64"] = z((B, d.MP), torch.float64)
         if self.spec.uses_adj:
-            self._adj_store = z((B * d.ADJS + 4,), torch.int32)   # 16 B of slack for the block-wide bulk copy
-            T["adj_bits"] = self._adj_store[:B * d.ADJS].view(B, d.ADJS)
+            B32 = (B + 31) // 32 * 32                             # whole tiles of 32 envs for the N <= 64 layout
+            self._adj_store = z((B32 * d.ADJS,), torch.int32)
+            T["adj_bits"] = self._adj_store
             if N <= 64 and self.spec.step_w == "f64":
                 T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
             elif self.spec.step_w == "f64":
@@ -232,7 +233,7 @@ class BatchedGraphEnv:
             u01 = up(np.array([i.u01 for i in instances], dtype=np.float64))  # multicast_routing.py:103 draw
         self.finalize_graphs(prepare=prepare, heuristics=self.is_eval_env and not have_heur, u01=u01)
 
-    def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None):
+    def finalize_graphs(self, prepare=True, heuristics=False, u01=None, features=None, maxdist_from_generator=False):
         """Derived static data after the CSR arrays are in place (load_instances / generate)."""
         L, d = self.lib, self.desc
         if self.spec.uses_adj or "rev" in self.t or "esrc" in self.t or "wmin" in self.t:
@@ -244,7 +245,7 @@ class BatchedGraphEnv:
             what |= PREP_INRANGE
         if heuristics and self.spec.heuristic_on_device(self.params):
             what |= PREP_HEURISTIC
-        if u01 is not None and self.env_id == "MulticastRouting-v0":
+        if (u01 is not None or maxdist_from_generator) and self.env_id == "MulticastRouting-v0":
             what |= PREP_MAXDIST
         if what:
             _native.check(L.ge_prepare(C.byref(d), what, _ptr(u01), self._stream()))
@@ -333,8 +334,21 @@ class BatchedGraphEnv:
             out.append(ins)
         return out
 
-    def generate(self, seed=0):
-        """Device-side instance generation (distribution parity with the reference's reset())."""
+    def adjacency_rows(self):
+        """uint32-as-int32 [B, N, NW] view/copy of the adjacency bit-matrix in env-major order, whatever the
+        device layout (include/graphenvs_b200.h: tiles of 32 envs for the lane-per-env family)."""
+        d, B, N = self.desc, self.B, self.N
+        a = self.t["adj_bits"]
+        tiled = N <= 64 and self.env_id in ("ShortestPath-v0", "LongestPath-v0", "TSP-v0", "MaxIndependentSet-v0",
+                                            "DensestSubgraph-v0") and not (d.flags & 8)
+        if tiled:
+            nt = (B + 31) // 32
+            return a[:nt * N * 32 * d.NW].view(nt, N, 32, d.NW).permute(0, 2, 1, 3).reshape(nt * 32, N, d.NW)[:B]
+        return a[:B * d.ADJS].view(B, d.ADJS)[:, :N * d.NW].view(B, N, d.NW)
+
+    def generate(self, seed=0, check=True):
+        """Device-side instance generation (distribution parity with the reference's reset()).  check=True reads back how
+        many envs needed the connected-by-construction fallback (one stream sync) into self.generate_fallbacks."""
         L, d, T = self.lib, self.desc, self.t
         w64 = T.get("w64")
         tmp64 = None
@@ -344,15 +358,21 @@ class BatchedGraphEnv:
             d.w64 = w64.data_ptr()
         _native.check(L.ge_generate(C.byref(d), int(seed), _ptr(T["row_ptr"]), _ptr(T["col"]), _ptr(w64),
                                     _ptr(T.get("w32")), self._stream()))
-        u01 = None
-        if self.env_id == "MulticastRouting-v0":
-            g = torch.Generator(device=self.device)
-            g.manual_seed(int(seed) + 12345 + d.env_id0)
-            u01 = torch.rand((self.B,), dtype=torch.float64, device=self.device, generator=g)
-        self.finalize_graphs(prepare=True, heuristics=self.is_eval_env, u01=u01)
+        # Multicast: the max_distance uniform (multicast_routing.py:103) is drawn by the generator per GLOBAL env id, so a
+        # rank-sliced batch gets the same distances as the single-GPU batch (ge_prepare reads it from max_dist32)
+        self.finalize_graphs(prepare=True, heuristics=self.is_eval_env, maxdist_from_generator=self.env_id == "MulticastRouting-v0")
         if tmp64 is not None:
             torch.cuda.current_stream(self.device).synchronize()
             self._sync_desc()
+        if check:
+            n = int(L.ge_generate_fallbacks(self._stream()))
+            if n < 0:
+                _native.check(n)
+            self.generate_fallbacks = n
+            if n:
+                import warnings
+                warnings.warn("ge_generate: %d of %d envs found no connected G(n=%d, m=%d) in 4096 draws and were emitted "
+                              "connected-by-construction (random tree / ring + random edges)" % (n, self.B, self.N, self.E))
 
     # ------------------------------------------------------------------ hot path
     def reset(self, select=None):
@@ -411,13 +431,22 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), None, C.byref(self._out), _ptr(h_reward),
                                             _ptr(h_flags), _ptr(h_cost), None, _ptr(h_mask_bits), self._stream()))
 
-    def host_stepper(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None, stream=None):
+    def host_stepper(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None, stream=None, pipelined=False,
+                     chunks=4):
         """Zero-argument callable = step_host on FIXED pinned buffers, arguments marshalled once.  On a
-        non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph."""
+        non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph.
+        pipelined=True: ge_step_host_pipelined -- the batch is stepped in `chunks` slices on parallel graph branches,
+        slice i's results cross PCIe while slice i+1 steps (needs a created stream; the byte mask is not returned)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
-        args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
-                _ptr(h_cost), _ptr(h_mask), _ptr(h_mask_bits), C.c_void_p(st.cuda_stream))
-        fn, check = self.lib.ge_step_host, _native.check
+        if pipelined and st.cuda_stream != 0 and h_mask is None:
+            args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
+                    _ptr(h_cost), _ptr(h_mask_bits), int(chunks), C.c_void_p(st.cuda_stream))
+            fn = self.lib.ge_step_host_pipelined
+        else:
+            args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
+                    _ptr(h_cost), _ptr(h_mask), _ptr(h_mask_bits), C.c_void_p(st.cuda_stream))
+            fn = self.lib.ge_step_host
+        check = _native.check
         keep = (h_actions, h_reward, h_flags, h_cost, h_mask, h_mask_bits, st)
 
         def call():
@@ -430,6 +459,22 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev),
                                             C.byref(self._out), _ptr(h_reward), _ptr(h_flags), _ptr(h_cost),
                                             _ptr(h_mask), _ptr(h_mask_bits), self._stream()))
+
+    def step_kernel_name(self, sampled=False):
+        """Name of the CUDA kernel ge_step (ge_step_sampled) dispatches this batch to."""
+        return self.lib.ge_step_kernel_name(C.byref(self.desc), int(bool(sampled))).decode()
+
+    def slice_desc(self, lo, count):
+        """C descriptor of the sub-batch [lo, lo+count) (ge_batch_slice): same memory, steppable on its own."""
+        out = _native.GeBatch()
+        _native.check(self.lib.ge_batch_slice(C.byref(self.desc), int(lo), int(count), C.byref(out)))
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.ge_step_host_release(C.byref(self.desc))   # cached CUDA graphs reference this batch's memory
+        except Exception:
+            pass
 
     def info(self, step=False):
         d = {"mask": self.mask, "mask_bits": self.t["mask_bits"], "heuristic_solution": self.t["heuristic"]}
@@ -461,6 +506,14 @@ class BatchedGraphEnv:
         ei = torch.empty((count, self.M, 2), dtype=torch.int64, device=self.device)
         _native.check(self.lib.ge_obs_graph(C.byref(self.desc), int(env_lo), int(count), _ptr(x), _ptr(ea), _ptr(ei), self._stream()))
         return x, ea, ei
+
+    def obs_nodes(self, env_lo=0, count=None, out=None):
+        """x float32[count, N, F] only: the node columns are the part of the observation a step changes."""
+        count = self.B - env_lo if count is None else count
+        if out is None:
+            out = torch.empty((count, self.N, self.F), dtype=torch.float32, device=self.device)
+        _native.check(self.lib.ge_obs_nodes(C.byref(self.desc), int(env_lo), int(count), _ptr(out), self._stream()))
+        return out
 
     def compute_features(self):
         if "features" not in self.t:

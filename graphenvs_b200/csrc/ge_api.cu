@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "ge_envs.cuh"
 
@@ -84,11 +85,11 @@ __global__ void __launch_bounds__(GE_WPB * 32, MINB) step_kernel(ge_batch d, int
         }
         if (r.status == GE_STEP_OK) {
             if (d.env_steps) d.env_steps[b] = nsteps + 1u;
-            d.acc[2 * (size_t)d.B + b] += r.reward;  // [4, B]: the per-step stream is one component wide
+            d.acc[2 * (size_t)d.acc_stride + b] += r.reward;  // [4, B]: the per-step stream is one component wide
             if (r.done) {
                 d.acc[b] += 1.0;
-                if (r.solved == 1) d.acc[(size_t)d.B + b] += 1.0;
-                if (r.sol == r.sol) d.acc[3 * (size_t)d.B + b] += r.sol;
+                if (r.solved == 1) d.acc[(size_t)d.acc_stride + b] += 1.0;
+                if (r.sol == r.sol) d.acc[3 * (size_t)d.acc_stride + b] += r.sol;
             }
         }
     }
@@ -148,6 +149,17 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
         if (lane == 0) d.wmin[b] = m;
     }
     if (!d.adj_bits) return;
+    if (adj_tiled(d)) {  // lane-per-env family: tiles of 32 envs (ge_common.cuh:adj_tiled); lane u owns row u (+32)
+        for (int u = lane; u < d.N; u += 32) {
+            uint32_t lo = 0, hi = 0;
+            for (int e = rp[u]; e < rp[u + 1]; ++e) {
+                int c = col[e];
+                if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32);
+            }
+            d.adj_bits[adj_word_index(d, b, u, 0)] = lo;
+            if (d.NW > 1) d.adj_bits[adj_word_index(d, b, u, 1)] = hi;
+        }
+    } else {
     uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
     for (int i = lane; i < d.ADJS; i += 32) adj[i] = 0;
     __syncwarp();
@@ -157,11 +169,13 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
             int c = col[e];
             atomicOr(&adj[(size_t)u * d.NW + (c >> 5)], 1u << (c & 31));
         }
-    if (d.wsort && d.w64) {  // weights in ascending-destination order per row: O(1) adj[u, v] lookup by bit rank
+    }
+    if (d.wsort && d.w64 && !adj_tiled(d)) {  // weights in ascending-destination order per row: O(1) adj[u, v] lookup by bit rank
         __syncwarp();
         __threadfence_block();
         const double *w64 = d.w64 + (size_t)b * d.MP;
         double *ws = d.wsort + (size_t)b * d.MP;
+        const uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
         for (int u = 0; u < d.N; ++u) {
             const int lo = rp[u], hi = rp[u + 1];
             const uint32_t *row = adj + (size_t)u * d.NW;
@@ -185,10 +199,46 @@ __global__ void __launch_bounds__(GE_WPB * 32) adjacency_kernel(ge_batch d) {
 }
 
 // Reference wire format (utils.py:87-88): [nodes.ravel | edges.ravel | edge_links.ravel] float32.
-// GRAPH = true writes the three sections to separate tensors instead -- x float32[count, N, F],
+// MODE 0 writes that flat vector; MODE 1 writes the three sections to separate tensors -- x float32[count, N, F],
 // edge_attr float32[count, M, Fe], edge_index int64[count, M, 2] -- i.e. what utils.devectorize_graph
-// (utils.py:14-23) would slice out of the flat vector, without the float32 round trip of the indices.
-template <bool GRAPH>
+// (utils.py:14-23) would slice out of the flat vector, without the float32 round trip of the indices; MODE 2
+// writes x only (the node columns are the part of the observation a step changes; edge tensors are static or,
+// for Multicast's IS_TAKEN column, one bit per step).  One CTA per env.  No per-element integer division and
+// no per-endpoint binary search: the (node, column) pair of a thread advances by a fixed stride, the edge
+// sections walk the CSR rows (warp per row), so the source of an edge is the row being walked.
+__device__ __forceinline__ float node_value(const ge_batch &d, int b, int v, int c, int dyn, const uint32_t *vis, const uint32_t *aux,
+                                            const uint32_t *tgt, int src, int dest, float maxd) {
+    const int N = d.N;
+    if (c >= dyn) return d.features ? d.features[((size_t)b * N + v) * 5 + (c - dyn)] : 0.f;
+    const bool bit = (vis[v >> 5] >> (v & 31)) & 1u;
+    switch (d.kind) {
+    case GE_SHORTEST_PATH: return c == 0 ? (float)bit : (float)(v == dest);
+    case GE_LONGEST_PATH:
+        if (c == 0) return (float)bit;
+        return (v == dest) ? 1.f : ((d.parenting == 0 && v == src) ? 2.f : 0.f);
+    case GE_STEINER_TREE: return c == 0 ? (float)bit : (float)((tgt[v >> 5] >> (v & 31)) & 1u);
+    case GE_TSP:
+        if (c == 0) return (float)bit;
+        if (c == 1) return (float)(v == 0);
+        return d.node_xy ? d.node_xy[((size_t)b * N + v) * 2 + (c - 2)] : 0.f;
+    case GE_MAX_INDEPENDENT_SET: return c == 0 ? d.node_cost[(size_t)b * N + v] : (float)bit;
+    case GE_DENSEST_SUBGRAPH: return (float)bit;
+    case GE_MULTICAST_ROUTING:
+        if (c == 0) return (float)bit;
+        if (c == 1) return (float)((tgt[v >> 5] >> (v & 31)) & 1u);
+        if (c == 2) return maxd;
+        return d.dist32[(size_t)b * N + v];
+    case GE_DISTRIBUTION_CENTER:
+        if (c == 0) return d.node_cost[(size_t)b * N + v];
+        if (c == 1) return (float)bit;
+        if (c == 2) return (float)((tgt[v >> 5] >> (v & 31)) & 1u);
+        if (c == 3) return (float)((aux[v >> 5] >> (v & 31)) & 1u);
+        return (float)d.max_distance;
+    }
+    return 0.f;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float *__restrict__ out, int L, float *__restrict__ out_e,
                                                 long long *__restrict__ out_i) {
     const int b = env_lo + blockIdx.x;
@@ -201,63 +251,54 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     default: dyn = 2;
     }
     const int F = dyn + 5, Fe = is_edge_kind(kind) ? 2 : 1;
-    float *o = out + (size_t)blockIdx.x * (GRAPH ? (size_t)N * F : (size_t)L);  // node section (GRAPH) or the whole flat vector
+    const int NF = N * F, MF = M * Fe;
+    float *o = out + (size_t)blockIdx.x * (MODE == 0 ? (size_t)L : (size_t)NF);  // the flat vector, or the node section
     const uint32_t *vis = d.node_bits + (size_t)b * d.NW;
     const uint32_t *aux = d.node_bits2 ? d.node_bits2 + (size_t)b * d.NW : nullptr;
     const uint32_t *tgt = d.target_bits ? d.target_bits + (size_t)b * d.NW : nullptr;
-    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
-    const int32_t *col = d.col + (size_t)b * d.MP;
-    const int NF = N * F, MF = M * Fe;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        float val = 0.f;
-        if (i < NF) {
-            int v = i / F, c = i - v * F;
-            bool bit = (vis[v >> 5] >> (v & 31)) & 1u;
-            if (c >= dyn) val = d.features ? d.features[((size_t)b * N + v) * 5 + (c - dyn)] : 0.f;
-            else switch (kind) {
-            case GE_SHORTEST_PATH: val = c == 0 ? (float)bit : (float)(v == d.dest[b]); break;
-            case GE_LONGEST_PATH:
-                if (c == 0) val = (float)bit;
-                else val = (v == d.dest[b]) ? 1.f : ((d.parenting == 0 && v == d.src[b]) ? 2.f : 0.f);
-                break;
-            case GE_STEINER_TREE: val = c == 0 ? (float)bit : (float)((tgt[v >> 5] >> (v & 31)) & 1u); break;
-            case GE_TSP:
-                if (c == 0) val = (float)bit;
-                else if (c == 1) val = (float)(v == 0);
-                else val = d.node_xy ? d.node_xy[((size_t)b * N + v) * 2 + (c - 2)] : 0.f;
-                break;
-            case GE_MAX_INDEPENDENT_SET: val = c == 0 ? d.node_cost[(size_t)b * N + v] : (float)bit; break;
-            case GE_DENSEST_SUBGRAPH: val = (float)bit; break;
-            case GE_MULTICAST_ROUTING:
-                if (c == 0) val = (float)bit;
-                else if (c == 1) val = (float)((tgt[v >> 5] >> (v & 31)) & 1u);
-                else if (c == 2) val = d.max_dist32[b];
-                else val = d.dist32[(size_t)b * N + v];
-                break;
-            case GE_DISTRIBUTION_CENTER:
-                if (c == 0) val = d.node_cost[(size_t)b * N + v];
-                else if (c == 1) val = (float)bit;
-                else if (c == 2) val = (float)((tgt[v >> 5] >> (v & 31)) & 1u);
-                else if (c == 3) val = (float)((aux[v >> 5] >> (v & 31)) & 1u);
-                else val = (float)d.max_distance;
-                break;
-            }
-        } else if (i < NF + MF) {
-            int j = i - NF, e = j / Fe, c = j - e * Fe;
-            if (c == 0) {
-                if (kind == GE_MAX_INDEPENDENT_SET || kind == GE_DENSEST_SUBGRAPH) val = 1.f;
-                else val = d.w32 ? d.w32[(size_t)b * d.MP + e] : (float)d.w64[(size_t)b * d.MP + e];
-            } else {
-                val = (kind == GE_MULTICAST_ROUTING) ? (float)((d.edge_bits[(size_t)b * d.MW + (e >> 5)] >> (e & 31)) & 1u) : 0.f;
-            }
-        } else {
-            int j = i - NF - MF, e = j >> 1;
-            int node = (j & 1) ? col[e] : edge_src(rp, N, e);
-            if (GRAPH) { out_i[(size_t)blockIdx.x * 2 * M + j] = node; continue; }
-            val = (float)node;
+    const bool seeded = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH;
+    const int src = seeded ? d.src[b] : 0, dest = seeded ? d.dest[b] : 0;
+    const float maxd = kind == GE_MULTICAST_ROUTING ? d.max_dist32[b] : 0.f;
+    {   // node section: element i = (v, c) with v = i / F; the pair advances by (blockDim / F, blockDim % F) per trip
+        int v = (int)threadIdx.x / F, c = (int)threadIdx.x - v * F;
+        const int dv = (int)blockDim.x / F, dc = (int)blockDim.x - dv * F;
+        for (int i = threadIdx.x; i < NF; i += blockDim.x) {
+            o[i] = node_value(d, b, v, c, dyn, vis, aux, tgt, src, dest, maxd);
+            v += dv; c += dc;
+            if (c >= F) { c -= F; ++v; }
         }
-        if (GRAPH && i >= NF) out_e[(size_t)blockIdx.x * MF + (i - NF)] = val;
-        else o[i] = val;
+    }
+    if (MODE == 2) return;
+    float *oe = MODE == 0 ? o + NF : out_e + (size_t)blockIdx.x * MF;
+    {   // edge feature section: column 0 = weight (1 for the unweighted kinds), column 1 = IS_TAKEN (Multicast) / zeros
+        const bool unit = kind == GE_MAX_INDEPENDENT_SET || kind == GE_DENSEST_SUBGRAPH;
+        const float *w32 = d.w32 ? d.w32 + (size_t)b * d.MP : nullptr;
+        const double *w64 = d.w64 ? d.w64 + (size_t)b * d.MP : nullptr;
+        const uint32_t *eb = kind == GE_MULTICAST_ROUTING ? d.edge_bits + (size_t)b * d.MW : nullptr;
+        for (int e = threadIdx.x; e < M; e += blockDim.x) {
+            const float w = unit ? 1.f : (w32 ? w32[e] : (float)w64[e]);
+            if (Fe == 1) oe[e] = w;
+            else {
+                const float tk = eb ? (float)((eb[e >> 5] >> (e & 31)) & 1u) : 0.f;
+                if (MODE == 1) reinterpret_cast<float2 *>(oe)[e] = make_float2(w, tk);   // own tensor: 8-byte aligned
+                else { oe[2 * e] = w; oe[2 * e + 1] = tk; }                             // flat vector: any float offset
+            }
+        }
+    }
+    {   // edge_links section: (source, destination) per directed edge, CSR order; one warp per row
+        const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+        const int32_t *col = d.col + (size_t)b * d.MP;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        float *ol = o + NF + MF;
+        long long *oi = out_i + (size_t)blockIdx.x * 2 * M;
+        for (int u = warp; u < N; u += nw) {
+            const int lo = rp[u], hi = rp[u + 1];
+            for (int e = lo + lane; e < hi; e += 32) {
+                const int v = col[e];
+                if (MODE == 1) reinterpret_cast<longlong2 *>(oi)[e] = make_longlong2(u, v);
+                else { ol[2 * e] = (float)u; ol[2 * e + 1] = (float)v; }
+            }
+        }
     }
 }
 
@@ -301,7 +342,8 @@ __global__ void __launch_bounds__(GE_WPB * 32) prep_sssp_kernel(ge_batch d, int 
                 far_tgt = fmax(far_tgt, __shfl_xor_sync(GE_FULL, far_tgt, o));
             }
             if (lane == 0) {
-                double md = __dadd_rn(__dmul_rn(u01[b], __dsub_rn(far_node, far_tgt)), far_tgt);
+                const double u = u01 ? u01[b] : (double)d.max_dist32[b];   // NULL: the draw ge_generate parked in max_dist32
+                double md = __dadd_rn(__dmul_rn(u, __dsub_rn(far_node, far_tgt)), far_tgt);
                 d.max_dist32[b] = (float)md;
             }
         }
@@ -367,7 +409,7 @@ __global__ void stats_kernel(ge_batch d, double *out4) {
     __shared__ double sh[4][32];
     double a[4] = {0, 0, 0, 0};
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < d.B; b += gridDim.x * blockDim.x)
-        for (int k = 0; k < 4; ++k) a[k] += d.acc[(size_t)k * d.B + b];
+        for (int k = 0; k < 4; ++k) a[k] += d.acc[(size_t)k * d.acc_stride + b];
     for (int k = 0; k < 4; ++k)
         for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(GE_FULL, a[k], o);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -405,6 +447,7 @@ static int check_batch(const ge_batch *d) {
     if (d->B <= 0 || d->N < 2 || d->M < 0) return fail(GE_ERR_ARG, "bad shape B=%d N=%d M=%d", d->B, d->N, d->M);
     if (d->N > 4096) return fail(GE_ERR_UNSUPPORTED, "N=%d > 4096 not supported", d->N);
     if (d->NW != (d->N + 31) / 32 || d->MW != (d->M + 31) / 32) return fail(GE_ERR_ARG, "layout not filled (call ge_fill_layout)");
+    if (d->acc_stride < d->B) return fail(GE_ERR_ARG, "acc_stride %d < B %d (call ge_fill_layout)", d->acc_stride, d->B);
     return GE_OK;
 }
 
@@ -421,7 +464,9 @@ static int launch_cfg(const ge_batch *d, int jobs, int *blocks, int *wpw, size_t
 int ge_grant_smem(const void *kernel, size_t smem) {
     static struct { const void *k; size_t granted; } table[32];
     static int n = 0;
+    static std::mutex mu;
     if (smem <= 48 * 1024) return GE_OK;
+    std::lock_guard<std::mutex> lock(mu);
     int i = 0;
     for (; i < n; ++i) if (table[i].k == kernel) break;
     if (i == n) {
@@ -446,15 +491,17 @@ int ge_fill_layout(ge_batch *d) {
     if (!d) return fail(GE_ERR_ARG, "null batch");
     d->NW = (d->N + 31) / 32;
     d->MW = (d->M + 31) / 32;
+    d->acc_stride = d->B;
+    d->reserved0 = 0;
     d->A = is_edge_kind(d->kind) ? d->M : d->N;
     d->AW = (d->A + 31) / 32;
     d->AP = (d->A + 15) & ~15;
     d->RP = (d->N + 1 + 3) & ~3;
     d->MP = (d->M + 3) & ~3;
     if (d->MP == 0) d->MP = 4;
-    // adjacency bit-matrix stride: for N <= 64 the lane-per-env kernels read lane-private rows from a
-    // block-contiguous shared-memory copy, so the stride is chosen bank-conflict free (odd number
-    // of words for 32-bit rows, 2 x odd for 64-bit rows); larger graphs keep 16-byte alignment.
+    // adjacency bit-matrix stride (words per env).  N <= 64 keeps the odd / 2 x odd stride of the first layout;
+    // the lane-per-env family stores those matrices in tiles of 32 envs (ge_common.cuh:adj_tiled), for which
+    // B rounded up to 32 envs of ADJS words is enough room.  Larger graphs keep 16-byte alignment.
     if (d->NW == 1) d->ADJS = d->N | 1;
     else if (d->NW == 2) d->ADJS = 2 * (d->N | 1);
     else d->ADJS = (d->N * d->NW + 3) & ~3;
@@ -496,7 +543,6 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
         GE_CUDA_OK(cudaGetLastError());
     }
     if ((what & 2) && d->kind == GE_MULTICAST_ROUTING) {
-        if (!u01) return fail(GE_ERR_ARG, "u01 required for Multicast max_distance");
         if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
         if ((rc = set_smem(prep_sssp_kernel, smem))) return rc;
         prep_sssp_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, 2, u01, wpw);
@@ -580,7 +626,7 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
-    obs_kernel<false><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d), nullptr, nullptr);
+    obs_kernel<0><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d), nullptr, nullptr);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }
@@ -590,12 +636,37 @@ int ge_obs_graph(const ge_batch *d, int env_lo, int count, float *x, float *edge
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
     if (!x || !edge_attr || !edge_index) return fail(GE_ERR_ARG, "null output buffers");
-    obs_kernel<true><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), edge_attr, (long long *)edge_index);
+    obs_kernel<1><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), edge_attr, (long long *)edge_index);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
+    if (!x) return fail(GE_ERR_ARG, "null output buffer");
+    obs_kernel<2><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), nullptr, nullptr);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }
 
 int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }
+
+const char *ge_step_kernel_name(const ge_batch *d, int sampled) {
+    static thread_local char name[96];
+    if (!d) return "";
+    const char *fam;
+    char shape[48] = "";
+    if (ge_lane_eligible(d)) { fam = "lane_step_kernel"; snprintf(shape, sizeof(shape), "STAGED=%d,SAMPLED=%d", (d->kind == GE_LONGEST_PATH || d->kind == GE_TSP) && d->parenting >= 2, sampled); }
+    else if (ge_group_eligible(d)) { fam = "group_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,G=%d", sampled, d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32); }
+    else if (ge_incr_eligible(d)) {
+        if (d->kind == GE_MAX_INDEPENDENT_SET) { fam = "incr_mis_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }
+        else { fam = "incr_tree_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,G=%d", sampled, d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32); }
+    } else { fam = "step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,MINB=%d", sampled, (d->kind == GE_DISTRIBUTION_CENTER && d->wcode && d->dfa) ? 6 : 4); }
+    snprintf(name, sizeof(name), "%s<%s>", fam, shape);
+    return name;
+}
 
 // The copy-mode body of ge_step_host: H2D actions, step, D2H results (enqueue only, no sync).
 static int step_host_enqueue(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
@@ -628,25 +699,107 @@ static int step_host_enqueue(const ge_batch *d, const int32_t *h_actions, int32_
     return GE_OK;
 }
 
-// ge_step_host is a fixed sequence (copy in, one kernel, copy out) over fixed buffers, called once per env
-// step: it is captured into a CUDA graph on first use and replayed with ONE launch call afterwards (three
-// to six driver calls otherwise).  The cache key is the whole descriptor plus every buffer pointer and the
-// stream; anything else re-captures.  Capture is impossible on the legacy default stream: direct path there.
+// ge_step_host / ge_step_host_pipelined are fixed sequences over fixed buffers, called once per env step: they are
+// captured into a CUDA graph on first use and replayed with ONE launch call afterwards.  The cache key is the whole
+// descriptor plus every buffer pointer, the stream and the chunk count; anything else re-captures.  The cache is
+// process-wide and mutex-guarded; ge_step_host_release drops a batch's entries.  Capture is impossible on the legacy
+// default stream: direct path there.
 namespace {
+constexpr int HSG_SLOTS = 8, HSG_MAX_CHUNKS = 8;
 struct HostStepGraph {
     ge_batch d;
     const void *p[10];
     cudaStream_t st;
+    int chunks;
     cudaGraphExec_t exec;
     bool valid;
 };
-HostStepGraph g_hsg[4];
+HostStepGraph g_hsg[HSG_SLOTS];
 int g_hsg_next = 0;
+std::mutex g_hsg_mu;
+cudaStream_t g_side[HSG_MAX_CHUNKS];
+cudaEvent_t g_fork, g_join[HSG_MAX_CHUNKS];
+bool g_side_ready = false;
+
+cudaGraphExec_t hsg_find(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks) {
+    for (HostStepGraph &g : g_hsg)
+        if (g.valid && g.st == st && g.chunks == chunks && memcmp(&g.d, d, sizeof(ge_batch)) == 0 && memcmp(g.p, key, sizeof(g.p)) == 0)
+            return g.exec;
+    return nullptr;
+}
+void hsg_insert(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks, cudaGraphExec_t exec) {
+    HostStepGraph &g = g_hsg[g_hsg_next];
+    g_hsg_next = (g_hsg_next + 1) % HSG_SLOTS;
+    if (g.valid) { cudaGraphExecDestroy(g.exec); g.valid = false; }
+    memcpy(&g.d, d, sizeof(ge_batch));
+    memcpy(g.p, key, sizeof(g.p));
+    g.st = st; g.chunks = chunks; g.exec = exec; g.valid = true;
+}
+
+// Waits for the stream by polling: a blocking synchronize parks the thread and pays the wake-up latency of an
+// interrupt (~10 us against a 40 us step); the results are needed by this very thread, so it spins.
+cudaError_t spin_until_done(cudaStream_t st) {
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return e;
+}
+
+// Write-back of one slice's results into the caller's pinned host arrays (UVA-mapped): every thread moves 16-byte
+// pieces, consecutive threads consecutive pieces => full 128-byte PCIe write transactions, all four arrays in one launch.
+__device__ __forceinline__ void copy_out(void *dst, const void *src, size_t bytes, int tid, int nthreads) {
+    const size_t n16 = bytes >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (size_t i = tid; i < n16; i += nthreads) d4[i] = s4[i];
+    const size_t done = n16 << 4;
+    for (size_t i = done + tid; i < bytes; i += nthreads) reinterpret_cast<unsigned char *>(dst)[i] = reinterpret_cast<const unsigned char *>(src)[i];
+}
+__global__ void __launch_bounds__(256) writeback_kernel(const float *reward, const ge_step_flags *flags, const double *cost, const uint32_t *mask_bits,
+                                                      float *h_reward, ge_step_flags *h_flags, double *h_cost, uint32_t *h_mask_bits, int n, int AW) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    copy_out(h_reward, reward, (size_t)n * 4, tid, nt);
+    copy_out(h_flags, flags, (size_t)n * 4, tid, nt);
+    if (h_cost) copy_out(h_cost, cost, (size_t)n * 8, tid, nt);
+    if (h_mask_bits) copy_out(h_mask_bits, mask_bits, (size_t)n * AW * 4, tid, nt);
+}
 }  // namespace
+
+int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
+    if (!d || !o) return fail(GE_ERR_ARG, "null batch");
+    if (lo < 0 || count <= 0 || lo + count > d->B || (lo & 31)) return fail(GE_ERR_ARG, "bad slice [%d, %d) of %d envs (lo must be a multiple of 32)", lo, lo + count, d->B);
+    *o = *d;
+    o->B = count;
+    o->env_id0 = d->env_id0 + lo;
+    const size_t b = (size_t)lo;
+#define ADV(field, per_env) if (d->field) o->field = d->field + b * (size_t)(per_env)
+    ADV(row_ptr, d->RP); ADV(col, d->MP); ADV(w32, d->MP); ADV(w64, d->MP);
+    if (d->adj_bits) o->adj_bits = d->adj_bits + (adj_tiled(*d) ? (b >> 5) * (size_t)d->N * 32 * d->NW : b * (size_t)d->ADJS);
+    ADV(rev, d->MP); ADV(esrc, d->MP); ADV(wsort, d->MP); ADV(wcode, d->MP); ADV(wmin, 1); ADV(wmat, (size_t)d->N * d->N);
+    ADV(src, 1); ADV(dest, 1); ADV(target_bits, d->NW); ADV(node_cost, d->N); ADV(node_xy, 2 * d->N); ADV(max_dist32, 1);
+    ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(heuristic, 1); ADV(features, 5 * d->N);
+    ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
+    ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
+    ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);
+#undef ADV
+    return GE_OK;   // dfa is shared by the whole batch; acc keeps the parent's component stride
+}
+
+int ge_step_host_release(const ge_batch *d) {
+    if (!d) return GE_OK;
+    std::lock_guard<std::mutex> lock(g_hsg_mu);
+    for (HostStepGraph &g : g_hsg)
+        if (g.valid && g.d.mask_bits == d->mask_bits) { cudaGraphExecDestroy(g.exec); g.valid = false; }
+    return GE_OK;
+}
 
 int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                  ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (!d) return fail(GE_ERR_ARG, "null batch");
     const size_t B = (size_t)d->B;
     if (!d_actions) {  // zero-copy: the kernel reads/writes the pinned host buffers itself
         if (!h_actions || !h_reward || !h_flags || !h_solution_cost) return fail(GE_ERR_ARG, "zero-copy step needs all host buffers");
@@ -667,31 +820,29 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
                            h_mask_bits};
     const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && !getenv("GE_NO_HOST_GRAPH");
     if (capturable) {
-        for (HostStepGraph &g : g_hsg)
-            if (g.valid && g.st == st && memcmp(&g.d, d, sizeof(ge_batch)) == 0 && memcmp(g.p, key, sizeof(key)) == 0) {
-                GE_CUDA_OK(cudaGraphLaunch(g.exec, st));
-                GE_CUDA_OK(cudaStreamSynchronize(st));
-                return GE_OK;
-            }
+        cudaGraphExec_t exec;
+        {
+            std::lock_guard<std::mutex> lock(g_hsg_mu);
+            exec = hsg_find(d, key, st, 0);
+        }
+        if (exec) {
+            GE_CUDA_OK(cudaGraphLaunch(exec, st));
+            GE_CUDA_OK(cudaStreamSynchronize(st));
+            return GE_OK;
+        }
         // first call for this (descriptor, buffers, stream): run once directly (also sets kernel attributes), then capture
         int rc = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
         if (rc) return rc;
         GE_CUDA_OK(cudaStreamSynchronize(st));
         // NOTE: the capture below does not execute anything; the call above already did this step.
+        std::lock_guard<std::mutex> lock(g_hsg_mu);
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc2 = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc2 == GE_OK && e == cudaSuccess && graph) {
-                HostStepGraph &g = g_hsg[g_hsg_next];
-                g_hsg_next = (g_hsg_next + 1) % 4;
-                if (g.valid) { cudaGraphExecDestroy(g.exec); g.valid = false; }
-                if (cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
-                    memcpy(&g.d, d, sizeof(ge_batch));
-                    memcpy(g.p, key, sizeof(key));
-                    g.st = st;
-                    g.valid = true;
-                }
+                cudaGraphExec_t ex = nullptr;
+                if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) hsg_insert(d, key, st, 0, ex);
             }
             if (graph) cudaGraphDestroy(graph);
             (void)cudaGetLastError();
@@ -703,6 +854,89 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
     int rc = step_host_enqueue(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask, h_mask_bits, st);
     if (rc) return rc;
     GE_CUDA_OK(cudaStreamSynchronize(st));
+    return GE_OK;
+}
+
+// One slice of the pipelined step on stream `s`: actions in, step, results out (enqueue only).
+static int pipelined_enqueue_slice(const ge_batch *d, int lo, int n, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
+                                   float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits, cudaStream_t s) {
+    ge_batch sl;
+    int rc = ge_batch_slice(d, lo, n, &sl);
+    if (rc) return rc;
+    ge_step_out so = {out->reward + lo, out->flags + lo, out->solution_cost + lo};
+    GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    rc = ge_step(&sl, d_actions + lo, &so, (void *)s);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * (16 + 4 * (size_t)d->AW);
+    int blocks = (int)((bytes / 16 + 255) / 256);
+    if (blocks > 32) blocks = 32;     // a handful of CTAs saturate PCIe; the rest of the GPU keeps stepping the next slice
+    if (blocks < 1) blocks = 1;
+    writeback_kernel<<<blocks, 256, 0, s>>>(so.reward, so.flags, so.solution_cost, sl.mask_bits, h_reward + lo, h_flags + lo,
+                                            h_solution_cost ? h_solution_cost + lo : nullptr,
+                                            h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
+int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                           ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits, int chunks, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (!h_actions || !d_actions || !out || !h_reward || !h_flags) return fail(GE_ERR_ARG, "null step buffers");
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return fail(GE_ERR_ARG, "ge_step_host_pipelined needs a created (capturable) stream");
+    if (chunks < 1) chunks = 1;
+    if (chunks > HSG_MAX_CHUNKS) chunks = HSG_MAX_CHUNKS;
+    int per = ((d->B + chunks - 1) / chunks + 127) & ~127;    // slice starts are multiples of 128 envs (tiles, vector alignment)
+    chunks = (d->B + per - 1) / per;
+    const void *key[10] = {h_actions, d_actions, out->reward, out->flags, out->solution_cost, h_reward, h_flags, h_solution_cost, nullptr, h_mask_bits};
+    cudaGraphExec_t exec;
+    {
+        std::lock_guard<std::mutex> lock(g_hsg_mu);
+        exec = hsg_find(d, key, st, chunks);
+    }
+    if (!exec) {
+        // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
+        // forked sequence for the following calls
+        for (int i = 0; i < chunks; ++i) {
+            const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
+            if ((rc = pipelined_enqueue_slice(d, lo, n, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
+        }
+        GE_CUDA_OK(cudaStreamSynchronize(st));
+        std::lock_guard<std::mutex> lock(g_hsg_mu);
+        if (!g_side_ready) {
+            for (int i = 0; i < HSG_MAX_CHUNKS; ++i) {
+                GE_CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
+                GE_CUDA_OK(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+            }
+            GE_CUDA_OK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+            g_side_ready = true;
+        }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc2 = GE_OK;
+            bool ok = cudaEventRecord(g_fork, st) == cudaSuccess;
+            for (int i = 0; ok && i < chunks && rc2 == GE_OK; ++i) {
+                const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
+                cudaStream_t s = i == 0 ? st : g_side[i];        // slice 0 stays on the origin stream
+                if (i) ok = ok && cudaStreamWaitEvent(s, g_fork, 0) == cudaSuccess;
+                rc2 = pipelined_enqueue_slice(d, lo, n, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s);
+                if (i) ok = ok && cudaEventRecord(g_join[i], s) == cudaSuccess && cudaStreamWaitEvent(st, g_join[i], 0) == cudaSuccess;
+            }
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (ok && rc2 == GE_OK && e == cudaSuccess && graph) {
+                cudaGraphExec_t ex = nullptr;
+                if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) hsg_insert(d, key, st, chunks, ex);
+            }
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+        } else {
+            (void)cudaGetLastError();
+        }
+        return GE_OK;
+    }
+    GE_CUDA_OK(cudaGraphLaunch(exec, st));
+    GE_CUDA_OK(spin_until_done(st));
     return GE_OK;
 }
 

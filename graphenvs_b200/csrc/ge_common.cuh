@@ -53,6 +53,24 @@ __device__ inline Scr carve(uint32_t *base, const ge_batch &d) {
     return s;
 }
 
+// Kinds the lane-per-env family (ge_lane.cu, N <= 64) steps.
+__host__ __device__ inline bool lane_kind(int kind) {
+    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_MAX_INDEPENDENT_SET ||
+           kind == GE_DENSEST_SUBGRAPH;
+}
+// Layout of adj_bits.  Default: env-major, [B, ADJS] = N rows of NW words per env.  For the lane-per-env family
+// (N <= 64) the matrix is stored in TILES of 32 envs, [ceil(B/32)][N rows][32 envs] of NW-word elements: lane l of a
+// warp reads row r_l of ITS env at element (r_l * 32 + l), so whatever rows the 32 lanes pick, their shared-memory
+// accesses fall on 32 different banks (env-major rows collided on 55 % of the wavefronts,
+// profiles/r01_lane_step_kernel_cfg2_v4_fused.md), and a block's tiles are still one contiguous bulk copy.
+__host__ __device__ inline bool adj_tiled(const ge_batch &d) {
+    return d.N <= 64 && lane_kind(d.kind) && !(d.flags & GE_FLAG_FORCE_WARP);
+}
+__host__ __device__ inline size_t adj_word_index(const ge_batch &d, int b, int row, int w) {
+    if (adj_tiled(d)) return ((((size_t)(b >> 5) * d.N + row) << 5) + (b & 31)) * d.NW + w;
+    return (size_t)b * d.ADJS + (size_t)row * d.NW + w;
+}
+
 __device__ inline bool tbit(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
 __device__ inline uint32_t tail_mask(int n, int w) {  // valid-bit mask of word w of an n-bit set
     int rem = n - (w << 5);

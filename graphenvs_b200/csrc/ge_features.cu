@@ -6,18 +6,305 @@
 // nx:algorithms/cluster.py).  All arithmetic in fp64, rounded to float32 at the end exactly like
 // `torch.tensor(sf)` (feature_extraction.py:36).
 //
-// One warp per environment.  Betweenness + closeness share one BFS per source; BFS frontiers are
-// bitsets, edge work goes through the load-balanced expand_set primitive; sigma / delta use
-// shared-memory fp64 atomics (sigma sums are integers < 2^53 => order-independent; delta sums
-// differ from networkx only by fp64 reassociation, ~1e-16 relative).
+// Round-2 design (features_cta_kernel, N <= 1024): ONE CTA PER ENV, ONE WARP PER BFS SOURCE.
+//   * the env's adjacency lives in shared memory as an N x NWP bit-matrix built once from the CSR
+//     (row stride NWP words = an odd number of 16-byte quads => lane-private rows are read with
+//     conflict-free 128-bit loads);
+//   * Brandes runs in PULL form on that matrix, without a single atomic: an unvisited node w joins
+//     level k iff row(w) & L_{k-1} != 0, and sigma[w] is the sum of sigma over exactly those bits;
+//     the backward sweep is delta[v] = sum over row(v) & L_{k} of sigma[v] * (1 + delta[w]) / sigma[w].
+//     Each lane owns the nodes lane, lane+32, ... and walks ITS unvisited ones, so a level costs
+//     (unvisited / 32) row scans restricted to the non-empty quads of the previous level set;
+//   * sources are independent: warp i takes sources i, i+W, ...; betweenness partials stay in
+//     registers (one per owned node) until the end; closeness falls out of the same search;
+//   * pagerank is a CTA-wide CSR mat-vec per iteration (G lanes per row), clustering is
+//     popcount(row_i & row_j) over the bit-matrix (the first version expanded N x M edges).
+// The first version (one warp per env, N serial sources, CSR expansion with shared fp64 atomics:
+// 190 us/env at TSP N=200 dense, 73 us/env at N=500) is kept as features_warp_kernel for N > 1024.
+// Sums are reassociated relative to networkx (sigma sums are integers < 2^53 => exact; delta and
+// pagerank differ by fp64 rounding, ~1e-16 relative; the tests compare at 1e-5 in float32).
 #include "ge_common.cuh"
 
 using namespace ge;
 
 extern "C" int ge_set_error(int code, const char *fmt, ...);
+int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 
 namespace {
 
+// ============================================================================================
+// CTA per env
+// ============================================================================================
+constexpr uint16_t UNVIS = 0xffffu;
+
+__host__ __device__ inline int feat_nwp(int NW) {  // row stride in words: whole quads, odd quad count
+    int q = (NW + 3) >> 2;
+    if (!(q & 1)) q += 1;
+    return q << 2;
+}
+__host__ __device__ inline int feat_warp_bytes(int N, int NWP) {  // sigma[N] f64 | delta[N] f64 | lv[NWP] u32 | D[N] u16
+    return (16 * N + 4 * NWP + 2 * N + 15) & ~15;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red, int W) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GE_FULL, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < W; ++w) t += red[w];
+    __syncthreads();
+    return t;
+}
+
+// sum of tab[base + i] over the set bits i of x
+__device__ __forceinline__ void gather_add(const double *tab, int base, uint32_t x, double &acc) {
+    while (x) {
+        acc += tab[base + __ffs(x) - 1];
+        x &= x - 1;
+    }
+}
+
+template <int NWMAX>
+__global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NWP, int warp_bytes, int G) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int b = blockIdx.x;
+    const int N = d.N, NW = d.NW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5, tid = threadIdx.x, NT = blockDim.x;
+    const int QN = NWP >> 2;
+    uint32_t *mat = smem;
+    char *wbase = reinterpret_cast<char *>(mat + (size_t)N * NWP);
+    double *sigma = reinterpret_cast<double *>(wbase + (size_t)warp * warp_bytes);
+    double *delta = sigma + N;
+    uint32_t *lv = reinterpret_cast<uint32_t *>(delta + N);
+    uint16_t *D = reinterpret_cast<uint16_t *>(lv + NWP);
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    float *out = d.features + (size_t)b * N * 5;
+
+    // ---------------- adjacency bit-matrix from the CSR
+    for (int i = tid; i < N * NWP; i += NT) mat[i] = 0;
+    for (int i = lane; i < NWP; i += 32) lv[i] = 0;
+    __syncthreads();
+    for (int u = warp; u < N; u += W) {
+        const int lo = rp[u], hi = rp[u + 1];
+        for (int e = lo + lane; e < hi; e += 32) {
+            const int c = col[e];
+            atomicOr(&mat[(size_t)u * NWP + (c >> 5)], 1u << (c & 31));
+        }
+    }
+    __syncthreads();
+
+    // ---------------- betweenness + closeness: one search per source, one warp per source
+    double bt[NWMAX];
+#pragma unroll
+    for (int j = 0; j < NWMAX; ++j) bt[j] = 0.0;
+
+    for (int s = warp; s < N; s += W) {
+        uint32_t unv = 0;  // bit j: node lane + 32 j exists and is unvisited
+        for (int j = 0; j < NW; ++j) {
+            const int v = lane + (j << 5);
+            if (v < N) { D[v] = UNVIS; unv |= 1u << j; }
+        }
+        if (lane < NW) lv[lane] = (lane == (s >> 5)) ? (1u << (s & 31)) : 0u;
+        __syncwarp();
+        if (lane == (s & 31)) { sigma[s] = 1.0; delta[s] = 0.0; D[s] = 0; unv &= ~(1u << (s >> 5)); }
+        uint32_t quads = 1u << (s >> 7);  // non-empty 128-bit groups of the previous level set
+        __syncwarp();
+        int level = 0, reached = 1;
+        long long totsp = 0;
+        while (reached < N) {  // forward sweep (_single_source_shortest_path_basic), pull form
+            ++level;
+            uint32_t newbits = 0, rem = unv;
+            while (rem) {
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int v = lane + (j << 5);
+                const uint4 *row = reinterpret_cast<const uint4 *>(mat + (size_t)v * NWP);
+                double sg = 0.0;
+                uint32_t q = quads;
+                while (q) {
+                    const int qi = __ffs(q) - 1;
+                    q &= q - 1;
+                    const uint4 r = row[qi];
+                    const uint4 l = reinterpret_cast<const uint4 *>(lv)[qi];
+                    const int base = qi << 7;
+                    gather_add(sigma, base, r.x & l.x, sg);
+                    gather_add(sigma, base + 32, r.y & l.y, sg);
+                    gather_add(sigma, base + 64, r.z & l.z, sg);
+                    gather_add(sigma, base + 96, r.w & l.w, sg);
+                }
+                if (sg > 0.0) { sigma[v] = sg; delta[v] = 0.0; D[v] = (uint16_t)level; newbits |= 1u << j; }
+            }
+            __syncwarp();
+            unv &= ~newbits;
+            uint32_t myword = 0;  // lane j keeps word j of the new level set
+            for (int j = 0; j < NW; ++j) {
+                const uint32_t wd = __ballot_sync(GE_FULL, (newbits >> j) & 1u);
+                if (lane == j) myword = wd;
+            }
+            const uint32_t nz = __ballot_sync(GE_FULL, myword != 0u);
+            if (!nz) { --level; break; }
+            if (lane < NW) lv[lane] = myword;
+            quads = 0;
+#pragma unroll
+            for (int qi = 0; qi < 8; ++qi)
+                if ((nz >> (4 * qi)) & 0xfu) quads |= 1u << qi;
+            const int cnt = __reduce_add_sync(GE_FULL, __popc(myword));
+            reached += cnt;
+            totsp += (long long)cnt * level;
+            __syncwarp();
+        }
+        if (lane == 0) {  // closeness: ((r-1)/totsp) * ((r-1)/(N-1)), 0 when totsp == 0
+            double cc = 0.0;
+            if (totsp > 0 && N > 1) {
+                cc = ((double)reached - 1.0) / (double)totsp;
+                cc *= ((double)reached - 1.0) / (double)(N - 1);
+            }
+            out[s * 5 + 2] = (float)cc;
+        }
+        // backward sweep (_accumulate_basic), pull form.  coeff[w] = (1 + delta[w]) / sigma[w] overwrites sigma[w]
+        // (sigma of level k is dead once its coefficients exist); delta[v] of level k-1 is the sum over its
+        // successors.  Level 1 only feeds delta[source], which betweenness never uses.
+        for (int k = level; k >= 2; --k) {
+            uint32_t myword = 0, prev = 0;
+            for (int j = 0; j < NW; ++j) {
+                const int v = lane + (j << 5);
+                const int dv = v < N ? (int)D[v] : -1;
+                const bool in = dv == k;
+                if (in) sigma[v] = (1.0 + delta[v]) / sigma[v];
+                if (dv == k - 1) prev |= 1u << j;
+                const uint32_t wd = __ballot_sync(GE_FULL, in);
+                if (lane == j) myword = wd;
+            }
+            const uint32_t nz = __ballot_sync(GE_FULL, myword != 0u);
+            if (lane < NW) lv[lane] = myword;
+            uint32_t qd = 0;
+#pragma unroll
+            for (int qi = 0; qi < 8; ++qi)
+                if ((nz >> (4 * qi)) & 0xfu) qd |= 1u << qi;
+            __syncwarp();
+            while (prev) {
+                const int j = __ffs(prev) - 1;
+                prev &= prev - 1;
+                const int v = lane + (j << 5);
+                const uint4 *row = reinterpret_cast<const uint4 *>(mat + (size_t)v * NWP);
+                double acc = 0.0;
+                uint32_t q = qd;
+                while (q) {
+                    const int qi = __ffs(q) - 1;
+                    q &= q - 1;
+                    const uint4 r = row[qi];
+                    const uint4 l = reinterpret_cast<const uint4 *>(lv)[qi];
+                    const int base = qi << 7;
+                    gather_add(sigma, base, r.x & l.x, acc);
+                    gather_add(sigma, base + 32, r.y & l.y, acc);
+                    gather_add(sigma, base + 64, r.z & l.z, acc);
+                    gather_add(sigma, base + 96, r.w & l.w, acc);
+                }
+                delta[v] = sigma[v] * acc;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < NWMAX; ++j) {
+            const int v = lane + (j << 5);
+            if (j < NW && v < N && v != s && D[v] != UNVIS) bt[j] += delta[v];
+        }
+        __syncwarp();
+    }
+    // betweenness: per-warp partials -> sum; degree column
+#pragma unroll
+    for (int j = 0; j < NWMAX; ++j) {
+        const int v = lane + (j << 5);
+        if (j < NW && v < N) sigma[v] = bt[j];
+    }
+    __syncthreads();
+    {
+        const double scale = (N - 1 >= 2) ? 1.0 / ((double)(N - 1) * (double)(N - 2)) : 1.0;  // _rescale, directed, normalized
+        for (int v = tid; v < N; v += NT) {
+            double t = 0.0;
+            for (int w = 0; w < W; ++w) t += reinterpret_cast<const double *>(wbase + (size_t)w * warp_bytes)[v];
+            out[v * 5 + 1] = (float)(t * scale);
+            out[v * 5 + 0] = (float)(2 * (rp[v + 1] - rp[v]));
+        }
+    }
+    __syncthreads();
+
+    // ---------------- pagerank (power iteration, scipy formulation); x / y / invS / red overlay the search scratch
+    {
+        double *x = reinterpret_cast<double *>(wbase), *y = x + N, *invS = y + N, *red = invS + N;
+        const bool weighted = (d.flags & GE_FLAG_WEIGHTED_PR) && d.w64;
+        const double *w64 = d.w64 ? d.w64 + (size_t)b * d.MP : nullptr;
+        const double p = 1.0 / (double)N, alpha = 0.85;
+        const int grp = tid / G, gl = tid % G, ngrp = NT / G;
+        int dangling = 0;
+        for (int v0 = 0; v0 < N; v0 += ngrp) {  // warp-uniform trip count: the group reductions below use the full mask
+            const int v = v0 + grp;
+            const bool live = v < N;
+            double S = 0.0;
+            if (live)
+                for (int e = rp[v] + gl; e < rp[v + 1]; e += G) S += weighted ? w64[e] : 1.0;
+            for (int o = G >> 1; o > 0; o >>= 1) S += __shfl_xor_sync(GE_FULL, S, o);
+            if (live && gl == 0) { invS[v] = S != 0.0 ? 1.0 / S : 0.0; x[v] = p; }
+            if (live && S == 0.0) dangling = 1;
+        }
+        dangling = __syncthreads_or(dangling);
+        for (int it = 0; it < 100; ++it) {
+            double dsum = 0.0;
+            if (dangling) {
+                for (int v = tid; v < N; v += NT)
+                    if (invS[v] == 0.0) dsum += x[v];
+                dsum = block_sum(dsum, red, W);
+            }
+            double err = 0.0;
+            for (int v0 = 0; v0 < N; v0 += ngrp) {
+                const int v = v0 + grp;
+                const bool live = v < N;
+                double acc = 0.0;  // (x @ A)[v] = sum_u x[u] * (invS[u] * w(u,v)); symmetric => in-neighbours = row v
+                if (live)
+                    for (int e = rp[v] + gl; e < rp[v + 1]; e += G) {
+                        const int u = col[e];
+                        const double a = invS[u] * (weighted ? w64[e] : 1.0);
+                        acc += a * x[u];
+                    }
+                for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(GE_FULL, acc, o);
+                if (live && gl == 0) {
+                    const double nx = alpha * (acc + dsum * p) + (1.0 - alpha) * p;
+                    err += fabs(nx - x[v]);
+                    y[v] = nx;
+                }
+            }
+            err = block_sum(err, red, W);
+            double *t = x; x = y; y = t;
+            if (err < (double)N * 1.0e-6) break;
+        }
+        for (int v = tid; v < N; v += NT) out[v * 5 + 3] = (float)x[v];
+    }
+
+    // ---------------- clustering: S_i = sum_{j in N(i)} |N(i) & N(j)|, c = S / (d (d-1)); the matrix is still intact
+    for (int i = warp; i < N; i += W) {
+        const int lo = rp[i], hi = rp[i + 1];
+        const uint4 *ri = reinterpret_cast<const uint4 *>(mat + (size_t)i * NWP);
+        int cnt = 0;
+        for (int e = lo + lane; e < hi; e += 32) {
+            const uint4 *rj = reinterpret_cast<const uint4 *>(mat + (size_t)col[e] * NWP);
+            for (int q = 0; q < QN; ++q) {
+                const uint4 a = ri[q], c = rj[q];
+                cnt += __popc(a.x & c.x) + __popc(a.y & c.y) + __popc(a.z & c.z) + __popc(a.w & c.w);
+            }
+        }
+        cnt = __reduce_add_sync(GE_FULL, cnt);
+        if (lane == 0) {
+            const long long dg = hi - lo;
+            const long long t = 8ll * cnt, dt = 2 * dg, db = dg;
+            out[i * 5 + 4] = (t == 0) ? 0.f : (float)((double)t / (double)((dt * (dt - 1) - 2 * db) * 2));
+        }
+    }
+}
+
+// ============================================================================================
+// One warp per env (round 1), kept for N > 1024 where the bit-matrix does not fit one CTA's shared memory
+// ============================================================================================
 struct FScr {
     double *sigma, *delta, *bt;  // [N] each
     int *D;                      // [N]
@@ -38,7 +325,7 @@ __device__ inline FScr fcarve(uint32_t *base, int N, int NW) {
     return s;
 }
 
-__global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int words_per_warp, int wpb) {
+__global__ void __launch_bounds__(GE_WPB * 32) features_warp_kernel(ge_batch d, int words_per_warp, int wpb) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * wpb + warp;
@@ -52,7 +339,6 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
     for (int v = lane; v < N; v += 32) s.bt[v] = 0.0;
     __syncwarp();
 
-    // ---------------- betweenness + closeness: one BFS per source
     for (int src = 0; src < N; ++src) {
         for (int v = lane; v < N; v += 32) { s.D[v] = -1; s.sigma[v] = 0.0; s.delta[v] = 0.0; }
         for (int w = lane; w < NW; w += 32) { s.f0[w] = 0; s.f1[w] = 0; }
@@ -62,7 +348,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
         int level = 0;
         long long totsp = 0;
         int reached = 1;
-        for (;;) {  // forward sweep (_single_source_shortest_path_basic)
+        for (;;) {
             double sg = 0.0;
             expand_set(
                 rp, s.f0, NW, lane, [&](int u) { sg = u >= 0 ? s.sigma[u] : 0.0; },
@@ -88,7 +374,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
             reached += cnt;
             totsp += (long long)cnt * level;
         }
-        if (lane == 0) {  // closeness: ((r-1)/totsp) * ((r-1)/(N-1)), 0 when totsp == 0
+        if (lane == 0) {
             double cc = 0.0;
             if (totsp > 0 && N > 1) {
                 cc = ((double)reached - 1.0) / (double)totsp;
@@ -96,7 +382,6 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
             }
             out[src * 5 + 2] = (float)cc;
         }
-        // backward sweep (_accumulate_basic): levels from the deepest up
         for (int L = level; L >= 1; --L) {
             for (int w = lane; w < NW; w += 32) {
                 uint32_t bits = 0;
@@ -113,7 +398,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
                 [&](int w) {
                     if (w >= 0) {
                         coeff = (1.0 + s.delta[w]) / s.sigma[w];
-                        s.bt[w] += s.delta[w];  // w != src at level >= 1; delta[w] is final here
+                        s.bt[w] += s.delta[w];
                     } else coeff = 0.0;
                 },
                 [&](int owner, int e, bool active) {
@@ -127,15 +412,13 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
         }
     }
     {
-        double scale = (N - 1 >= 2) ? 1.0 / ((double)(N - 1) * (double)(N - 2)) : 1.0;  // _rescale, directed, normalized
+        double scale = (N - 1 >= 2) ? 1.0 / ((double)(N - 1) * (double)(N - 2)) : 1.0;
         for (int v = lane; v < N; v += 32) {
             out[v * 5 + 1] = (float)(s.bt[v] * scale);
             out[v * 5 + 0] = (float)(2 * (rp[v + 1] - rp[v]));
         }
     }
     __syncwarp();
-
-    // ---------------- pagerank (power iteration, scipy formulation)
     {
         double *x = s.sigma, *y = s.delta, *invS = s.bt;
         const bool weighted = (d.flags & GE_FLAG_WEIGHTED_PR) && d.w64;
@@ -154,7 +437,7 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
             for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(GE_FULL, dsum, o);
             double err = 0.0;
             for (int v = lane; v < N; v += 32) {
-                double acc = 0.0;  // (x @ A)[v] = sum_u x[u] * (invS[u] * w(u,v)); symmetric => in-neighbours = row v
+                double acc = 0.0;
                 for (int e = rp[v]; e < rp[v + 1]; ++e) {
                     int u = col[e];
                     double a = invS[u] * (weighted ? w64[e] : 1.0);
@@ -172,8 +455,6 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
         for (int v = lane; v < N; v += 32) out[v * 5 + 3] = (float)x[v];
         __syncwarp();
     }
-
-    // ---------------- clustering: S_i = sum_{j in N(i)} |N(i) & N(j)|, c = S / (d (d-1))
     for (int i = 0; i < N; ++i) {
         int lo = rp[i], hi = rp[i + 1];
         for (int w = lane; w < NW; w += 32) s.lvl[w] = 0;
@@ -196,22 +477,54 @@ __global__ void __launch_bounds__(GE_WPB * 32) features_kernel(ge_batch d, int w
     }
 }
 
-}  // namespace
-
-extern "C" int ge_features(const ge_batch *d, void *stream) {
-    if (!d || !d->features) return ge_set_error(GE_ERR_ARG, "ge_features: features buffer is null");
+static int launch_warp_family(const ge_batch *d, cudaStream_t st) {
     int wpw = feat_words(d->N, d->NW);
     size_t per_warp = (size_t)wpw * sizeof(uint32_t);
     int wpb = (int)((200 * 1024) / per_warp);
     if (wpb < 1) return ge_set_error(GE_ERR_UNSUPPORTED, "ge_features: N=%d too large for shared scratch", d->N);
     if (wpb > GE_WPB) wpb = GE_WPB;
     size_t smem = per_warp * wpb;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-    features_kernel<<<(d->B + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(*d, wpw, wpb);
+    int rc = ge_grant_smem((const void *)features_warp_kernel, smem);
+    if (rc) return rc;
+    features_warp_kernel<<<(d->B + wpb - 1) / wpb, wpb * 32, smem, st>>>(*d, wpw, wpb);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "features_kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "features_warp_kernel launch: %s", cudaGetErrorString(e));
+    return GE_OK;
+}
+
+}  // namespace
+
+extern "C" int ge_features(const ge_batch *d, void *stream) {
+    if (!d || !d->features) return ge_set_error(GE_ERR_ARG, "ge_features: features buffer is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = d->N, NW = d->NW;
+    if (N > 1024 || (d->flags & GE_FLAG_FORCE_WARP)) return launch_warp_family(d, st);
+    const int NWP = feat_nwp(NW), wb = feat_warp_bytes(N, NWP);
+    const size_t mat_bytes = (size_t)N * NWP * 4;
+    const size_t budget = 227 * 1024;
+    int W = (N + 7) / 8;                         // sources per warp >= 8 where there are that many
+    if (W < 2) W = 2;                            // the pagerank overlay needs two warps' scratch
+    if (W > 16) W = 16;
+    while (W > 2 && mat_bytes + (size_t)W * wb + 8 * 16 > budget) --W;
+    const size_t need = mat_bytes + (size_t)W * wb + 8 * 16;
+    const size_t overlay = 3 * (size_t)N * 8 + 8 * 16;           // x, y, invS, red[W]
+    size_t smem = mat_bytes + (need - mat_bytes > overlay ? need - mat_bytes : overlay);
+    if (smem > budget) return launch_warp_family(d, st);
+    const int avg = N > 0 ? d->M / N : 1;
+    int G = 1;
+    while (G < 32 && 2 * G <= avg / 2) G <<= 1;                   // lanes per CSR row in the pagerank mat-vec
+    const void *kernel;
+    if (NW <= 2) kernel = (const void *)features_cta_kernel<2>;
+    else if (NW <= 4) kernel = (const void *)features_cta_kernel<4>;
+    else if (NW <= 8) kernel = (const void *)features_cta_kernel<8>;
+    else if (NW <= 16) kernel = (const void *)features_cta_kernel<16>;
+    else kernel = (const void *)features_cta_kernel<32>;
+    int rc = ge_grant_smem(kernel, smem);
+    if (rc) return rc;
+    ge_batch dd = *d;
+    int nwp = NWP, wbytes = wb, g = G;
+    void *args[] = {&dd, &nwp, &wbytes, &g};
+    cudaError_t e = cudaLaunchKernel(kernel, dim3((unsigned)d->B), dim3((unsigned)(W * 32)), args, smem, st);
+    if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "features_cta_kernel launch: %s", cudaGetErrorString(e));
     return GE_OK;
 }

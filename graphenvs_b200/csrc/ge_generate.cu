@@ -8,7 +8,9 @@
 // removal of node 0 disconnects them, tsp.py:60-71), weights k/10 with k~U{3..9} per undirected
 // edge, terminals uniform without replacement.  RNG is a counter-based hash, so instance b of a
 // batch is a pure function of (seed, env_id0 + b) -- rank-sliced batches equal the single-GPU batch.
-// Rows are emitted with ascending neighbour ids (the reference's insertion order is arbitrary).
+// Rows are emitted in INSERTION order like the reference's list(DiGraph.edges) (which edge wins np.argmin ties under
+// Multicast parenting >= 3 depends on it).  A draw whose rejection loop runs out of attempts is replaced by a
+// connected-by-construction graph and counted (ge_generate_fallbacks); spatial TSP draws coordinates (tsp.py:80-86).
 #include <cstdio>
 
 #include "ge_common.cuh"
@@ -16,6 +18,7 @@
 using namespace ge;
 
 extern "C" int ge_set_error(int code, const char *fmt, ...);
+int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 
 namespace {
 
@@ -60,6 +63,10 @@ __device__ inline int reach_count(const uint32_t *mat, int NW, int lane, const u
     return __reduce_add_sync(GE_FULL, c);
 }
 
+__device__ unsigned int g_generate_fallbacks;   // envs of the most recent ge_generate that exhausted the rejection loop
+
+#define GE_GEN_MAX_ATTEMPTS 4096
+
 __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col,
                                 double *__restrict__ w64, float *__restrict__ w32, int words_per_warp, int wpb, int weighted) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -70,13 +77,49 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
     const int n = (d.kind == GE_DENSEST_SUBGRAPH) ? N - 1 : N;  // densest_subgraph.py:59-65: node N-1 isolated
     uint32_t *mat = smem + (size_t)warp * words_per_warp;
     uint32_t *allowed = mat + (size_t)N * NW, *reach = allowed + NW, *frontier = reach + NW, *next = frontier + NW;
+    int *cursor = reinterpret_cast<int *>(next + NW);                       // [N]  next free CSR slot of every row
+    uint32_t *elist = reinterpret_cast<uint32_t *>(cursor + N);             // [E]  accepted edges in INSERTION order, (u << 16) | v
     const uint64_t gid = (uint64_t)(uint32_t)(d.env_id0 + b);
     const long long max_edges = (long long)n * (n - 1) / 2;
+    const bool complete = E >= max_edges;
 
-    for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
+    // i.i.d. endpoint pairs, self-loops / duplicates rejected, until E edges (nx.gnm_random_graph); 32 proposals per round,
+    // accepted ones appended in (round, lane) order.  `count` edges are already present.
+    auto sample_edges = [&](int count, uint32_t attempt) {
+        for (uint32_t it = 0; count < E; ++it) {
+            const int need = min(32, E - count);
+            bool isnew = false;
+            int u = 0, v = 0;
+            if (lane < need) {
+                uint64_t r = mix64(seed, gid, ((uint64_t)attempt << 40) | ((uint64_t)it << 5) | (uint64_t)lane);
+                u = (int)bounded((uint32_t)r, (uint32_t)n); v = (int)bounded((uint32_t)(r >> 32), (uint32_t)n);
+                if (u != v) {
+                    int a = min(u, v), c = max(u, v);
+                    uint32_t bit = 1u << (c & 31);
+                    uint32_t old = atomicOr(&mat[(size_t)a * NW + (c >> 5)], bit);
+                    if (!(old & bit)) {
+                        isnew = true;
+                        atomicOr(&mat[(size_t)c * NW + (a >> 5)], 1u << (a & 31));
+                    }
+                }
+            }
+            const unsigned acc = __ballot_sync(GE_FULL, isnew);
+            if (isnew) elist[count + __popc(acc & ((1u << lane) - 1u))] = ((uint32_t)u << 16) | (uint32_t)v;
+            count += __popc(acc);
+        }
+        __syncwarp();
+    };
+    auto add_edge_lane0 = [&](int u, int v, int k) {   // called by one lane
+        mat[(size_t)u * NW + (v >> 5)] |= 1u << (v & 31);
+        mat[(size_t)v * NW + (u >> 5)] |= 1u << (u & 31);
+        elist[k] = ((uint32_t)u << 16) | (uint32_t)v;
+    };
+
+    bool accepted = false;
+    for (uint32_t attempt = 0; attempt < GE_GEN_MAX_ATTEMPTS && !accepted; ++attempt) {
         for (int i = lane; i < N * NW; i += 32) mat[i] = 0;
         __syncwarp();
-        if (E >= max_edges) {  // complete_graph, no randomness (nx:generators/random_graphs.py:294-296)
+        if (complete) {  // complete_graph, no randomness (nx:generators/random_graphs.py:294-296)
             for (int u = lane; u < n; u += 32)
                 for (int w = 0; w < NW; ++w) {
                     uint32_t m = tail_mask(n, w);
@@ -84,25 +127,7 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
                     mat[(size_t)u * NW + w] = m;
                 }
         } else {
-            int count = 0;
-            for (uint32_t it = 0; count < E; ++it) {
-                int need = min(32, E - count);
-                bool isnew = false;
-                if (lane < need) {
-                    uint64_t r = mix64(seed, gid, ((uint64_t)attempt << 40) | ((uint64_t)it << 5) | (uint64_t)lane);
-                    int u = (int)bounded((uint32_t)r, (uint32_t)n), v = (int)bounded((uint32_t)(r >> 32), (uint32_t)n);
-                    if (u != v) {
-                        int a = min(u, v), c = max(u, v);
-                        uint32_t bit = 1u << (c & 31);
-                        uint32_t old = atomicOr(&mat[(size_t)a * NW + (c >> 5)], bit);
-                        if (!(old & bit)) {
-                            isnew = true;
-                            atomicOr(&mat[(size_t)c * NW + (a >> 5)], 1u << (a & 31));
-                        }
-                    }
-                }
-                count += __popc(__ballot_sync(GE_FULL, isnew));
-            }
+            sample_edges(0, attempt);
         }
         __syncwarp();
         for (int w = lane; w < NW; w += 32) allowed[w] = tail_mask(n, w);
@@ -120,14 +145,51 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
             __syncwarp();
             if (n > 1 && reach_count(mat, NW, lane, allowed, reach, frontier, next, 1) != n - 1) continue;
         }
-        break;
+        accepted = true;
+    }
+    if (!accepted) {
+        // The reference would keep drawing; for (n, m) where a connected draw is this rare the loop would never end
+        // here either.  Emit a graph that is valid BY CONSTRUCTION instead and count it (ge_generate_fallbacks): a
+        // random recursive tree (TSP: a Hamiltonian ring, which also has no degree-1 node and stays connected without
+        // the start) plus uniformly drawn extra edges.
+        for (int i = lane; i < N * NW; i += 32) mat[i] = 0;
+        __syncwarp();
+        int base = 0;
+        if (lane == 0) {
+            atomicAdd(&g_generate_fallbacks, 1u);
+            if (d.kind == GE_TSP) {
+                for (int v = 0; v < n; ++v) add_edge_lane0(v, (v + 1) % n, v);
+            } else {
+                for (int v = 1; v < n; ++v) add_edge_lane0((int)bounded((uint32_t)(mix64(seed ^ 0xA24BAED4963EE407ull, gid, (uint64_t)v) >> 32), (uint32_t)v), v, v - 1);
+            }
+        }
+        base = d.kind == GE_TSP ? n : n - 1;
+        __syncwarp();
+        sample_edges(min(base, E), GE_GEN_MAX_ATTEMPTS);
     }
 
-    // ---- CSR (ascending neighbour ids) + weights
+    // ---- CSR + weights.  Row u lists its neighbours in the order the undirected edges touching u were INSERTED
+    //      (list(G.to_directed().edges) of the reference: source-sorted, insertion order inside a row); a complete
+    //      graph's insertion order (itertools.combinations) is ascending neighbour id.
     int32_t *rp = row_ptr + (size_t)b * d.RP;
     int32_t *cl = col + (size_t)b * d.MP;
     double *wd = w64 ? w64 + (size_t)b * d.MP : nullptr;
     float *wf = w32 ? w32 + (size_t)b * d.MP : nullptr;
+    // spatial TSP (tsp.py:80-86): coordinates U(0,10)^2, weight = Euclidean distance in fp64
+    const bool spatial = d.kind == GE_TSP && d.node_xy != nullptr;
+    const uint64_t xyseed = seed ^ 0x2545F4914F6CDD1Dull;
+    auto coord = [&](int v, int axis) {
+        return (double)(mix64(xyseed, gid, ((uint64_t)v << 1) | (uint64_t)axis) >> 11) * (1.0 / 9007199254740992.0) * 10.0;
+    };
+    auto edge_weight = [&](int u, int v) {
+        if (spatial) {
+            const double dx = coord(u, 0) - coord(v, 0), dy = coord(u, 1) - coord(v, 1);
+            return sqrt(dx * dx + dy * dy);
+        }
+        if (!weighted || d.kind == GE_MAX_INDEPENDENT_SET || d.kind == GE_DENSEST_SUBGRAPH) return 1.0;
+        uint64_t r = mix64(seed ^ 0x5851F42D4C957F2Dull, gid, ((uint64_t)min(u, v) << 32) | (uint64_t)max(u, v));
+        return (double)(3 + (int)bounded((uint32_t)(r >> 32), 7u)) / 10.0;  // randint(3,10)/10.0
+    };
     int running = 0;
     if (lane == 0) rp[0] = 0;
     for (int base = 0; base < N; base += 32) {
@@ -143,24 +205,52 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
         if (u < N) {
             rp[u + 1] = running + inc;
             int e = running + inc - deg;
-            for (int w = 0; w < NW; ++w) {
-                uint32_t bits = mat[(size_t)u * NW + w];
-                while (bits) {
-                    int v = (w << 5) + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    cl[e] = v;
-                    double wt = 1.0;
-                    if (weighted && d.kind != GE_MAX_INDEPENDENT_SET && d.kind != GE_DENSEST_SUBGRAPH) {
-                        uint64_t r = mix64(seed ^ 0x5851F42D4C957F2Dull, gid, ((uint64_t)min(u, v) << 32) | (uint64_t)max(u, v));
-                        wt = (double)(3 + (int)bounded((uint32_t)(r >> 32), 7u)) / 10.0;  // randint(3,10)/10.0
+            cursor[u] = e;
+            if (complete)
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t bits = mat[(size_t)u * NW + w];
+                    while (bits) {
+                        int v = (w << 5) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        cl[e] = v;
+                        double wt = edge_weight(u, v);
+                        if (wd) wd[e] = wt;
+                        if (wf) wf[e] = (float)wt;
+                        ++e;
                     }
-                    if (wd) wd[e] = wt;
-                    if (wf) wf[e] = (float)wt;
-                    ++e;
                 }
-            }
         }
         running += __shfl_sync(GE_FULL, inc, 31);
+    }
+    __syncwarp();
+    if (!complete) {
+        for (int k0 = 0; k0 < E; k0 += 32) {   // 32 edges per trip; a node met several times in one trip is ranked by slot order
+            const int k = k0 + lane;
+            const bool valid = k < E;
+            const uint32_t pr = valid ? elist[k] : 0xffffffffu;
+            const int a = (int)(pr >> 16), c = (int)(pr & 0xffffu);
+            int ra = 0, rc = 0;
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t pj = __shfl_sync(GE_FULL, pr, j);
+                if (j < lane && pj != 0xffffffffu) {
+                    const int aj = (int)(pj >> 16), cj = (int)(pj & 0xffffu);
+                    ra += (aj == a) + (cj == a);
+                    rc += (aj == c) + (cj == c);
+                }
+            }
+            int pa = 0, pc = 0;
+            if (valid) { pa = cursor[a] + ra; pc = cursor[c] + rc; }
+            __syncwarp();
+            if (valid) {
+                const double wt = edge_weight(a, c);
+                cl[pa] = c; cl[pc] = a;
+                if (wd) { wd[pa] = wt; wd[pc] = wt; }
+                if (wf) { wf[pa] = (float)wt; wf[pc] = (float)wt; }
+                atomicAdd(&cursor[a], 1);
+                atomicAdd(&cursor[c], 1);
+            }
+            __syncwarp();
+        }
     }
     for (int e = d.M + lane; e < d.MP; e += 32) { cl[e] = 0; if (wd) wd[e] = 0; if (wf) wf[e] = 0; }
 
@@ -209,8 +299,14 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
         }
     }
     if (d.node_xy)
-        for (int i = lane; i < 2 * N; i += 32) d.node_xy[(size_t)b * N * 2 + i] = 0.f;
+        for (int i = lane; i < 2 * N; i += 32) d.node_xy[(size_t)b * N * 2 + i] = spatial ? (float)coord(i >> 1, i & 1) : 0.f;
+    // Multicast max_distance draw (multicast_routing.py:103 np.random.rand()): a pure function of (seed, global env id),
+    // parked in max_dist32 until ge_prepare(bit 1, u01 = NULL) turns it into the distance
+    if (d.kind == GE_MULTICAST_ROUTING && d.max_dist32 && lane == 0)
+        d.max_dist32[b] = (float)((double)(mix64(tseed, gid, 3) >> 40) * (1.0 / 16777216.0));
 }
+
+__global__ void clear_fallbacks_kernel() { g_generate_fallbacks = 0; }
 
 }  // namespace
 
@@ -220,18 +316,29 @@ extern "C" int ge_generate(const ge_batch *d, uint64_t seed, int32_t *row_ptr, i
     const int E = d->M / 2;
     const int n = d->kind == GE_DENSEST_SUBGRAPH ? d->N - 1 : d->N;
     if (E < n - 1) return ge_set_error(GE_ERR_ARG, "ge_generate: n_edges=%d < n-1, graph cannot be connected", E);
-    int wpw = (d->N * d->NW + 4 * d->NW + 3) & ~3;
+    if (d->kind == GE_TSP && E < n && n > 2) return ge_set_error(GE_ERR_ARG, "ge_generate: TSP needs n_edges >= n_nodes (no degree-1 node, tsp.py:64-65)");
+    const bool complete = (long long)E >= (long long)n * (n - 1) / 2;      // no edge list needed: rows are ascending
+    int wpw = (d->N * d->NW + 4 * d->NW + d->N + (complete ? 0 : E) + 3) & ~3;
     size_t per_warp = (size_t)wpw * sizeof(uint32_t);
     int wpb = (int)((200 * 1024) / per_warp);
     if (wpb < 1) return ge_set_error(GE_ERR_UNSUPPORTED, "ge_generate: graph too large");
     if (wpb > GE_WPB) wpb = GE_WPB;
     size_t smem = per_warp * wpb;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
+    int rc = ge_grant_smem((const void *)generate_kernel, smem);
+    if (rc) return rc;
     int weighted = (d->flags & GE_FLAG_UNWEIGHTED) ? 0 : 1;
+    clear_fallbacks_kernel<<<1, 1, 0, (cudaStream_t)stream>>>();
     generate_kernel<<<(d->B + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(*d, seed, row_ptr, col, w64, w32, wpw, wpb, weighted);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "generate_kernel launch: %s", cudaGetErrorString(e));
+}
+
+// Number of envs of the most recent ge_generate on `stream` whose rejection loop ran out of attempts and that were
+// emitted as connected-by-construction graphs instead (synchronises the stream).  0 for every BASELINE configuration.
+extern "C" int ge_generate_fallbacks(void *stream) {
+    unsigned int n = 0;
+    cudaError_t e = cudaMemcpyFromSymbolAsync(&n, g_generate_fallbacks, sizeof(n), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "ge_generate_fallbacks: %s", cudaGetErrorString(e));
+    return (int)n;
 }

@@ -290,11 +290,11 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
         }
         if (status == GE_STEP_OK) {
             if (d.env_steps) d.env_steps[b] = nsteps + 1u;
-            d.acc[2 * (size_t)d.B + b] += reward;
+            d.acc[2 * (size_t)d.acc_stride + b] += reward;
             if (done) {
                 d.acc[b] += 1.0;
-                if (solved == 1) d.acc[(size_t)d.B + b] += 1.0;
-                if (sol == sol) d.acc[3 * (size_t)d.B + b] += sol;
+                if (solved == 1) d.acc[(size_t)d.acc_stride + b] += 1.0;
+                if (sol == sol) d.acc[3 * (size_t)d.acc_stride + b] += sol;
             }
         }
     }

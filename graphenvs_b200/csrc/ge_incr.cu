@@ -108,11 +108,11 @@ __device__ __forceinline__ void publish(const ge_batch &d, const ge_step_out &ou
     }
     if (r.status == GE_STEP_OK) {
         if (d.env_steps) d.env_steps[b] = nsteps + 1u;
-        d.acc[2 * (size_t)d.B + b] += r.reward;
+        d.acc[2 * (size_t)d.acc_stride + b] += r.reward;
         if (r.done) {
             d.acc[b] += 1.0;
-            if (r.solved == 1) d.acc[(size_t)d.B + b] += 1.0;
-            if (r.sol == r.sol) d.acc[3 * (size_t)d.B + b] += r.sol;
+            if (r.solved == 1) d.acc[(size_t)d.acc_stride + b] += 1.0;
+            if (r.sol == r.sol) d.acc[3 * (size_t)d.acc_stride + b] += r.sol;
         }
     }
 }
@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
         if (lane == 0) publish(d, out, b, a, r, nsteps);
         return;
     }
-    const bool ok = a >= 0 && a < d.A && ((d.mask_bits[(size_t)b * d.AW + (a >> 5)] >> (a & 31)) & 1u);
+    // one lane reads the validity bit and broadcasts it: the mask words are mutated further down by other lanes of the
+    // group, and every lane must take the same branch here
+    uint32_t okw = 0;
+    if (lane == 0 && a >= 0 && a < d.A) okw = (d.mask_bits[(size_t)b * d.AW + (a >> 5)] >> (a & 31)) & 1u;
+    const bool ok = g.shfl(okw, 0) != 0u;
     if (!ok) {
         r.status = GE_STEP_INVALID; r.has_mask = 0;
         if (lane == 0) publish(d, out, b, a, r, nsteps);

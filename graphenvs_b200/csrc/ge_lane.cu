@@ -6,8 +6,9 @@
 // of a warp is 32-wide redundant.  Here an env's node sets are single 64-bit registers of ONE
 // thread, a warp advances 32 envs, and the only graph data a step needs -- the N x NW adjacency
 // bit-matrix -- is staged for the whole block with ONE bulk asynchronous copy (cp.async.bulk,
-// SASS UBLKCP) into shared memory while the threads load their scalar state.  Per-env stride
-// ADJS is chosen so that lane-private rows fall on distinct banks (ge_fill_layout).
+// SASS UBLKCP) into shared memory while the threads load their scalar state.  The matrix is stored in
+// tiles of 32 envs ([tile][row][env], ge_common.cuh:adj_tiled) so that the lane-private row reads of a
+// warp never collide on a shared-memory bank, whichever rows the 32 searches are at.
 //
 // Semantics are those of ge_envs.cuh (same reference line map); tests run every N <= 64 case
 // through both paths (GE_FLAG_FORCE_WARP).
@@ -47,33 +48,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-__host__ __device__ inline bool lane_kind(int kind) {
-    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_MAX_INDEPENDENT_SET ||
-           kind == GE_DENSEST_SUBGRAPH;
-}
 // kinds/modes whose mask needs reachability over the residual graph => whole bit-matrix staged
 __host__ __device__ inline bool lane_stages(const ge_batch &d) {
     return (d.kind == GE_LONGEST_PATH || d.kind == GE_TSP) && d.parenting >= 2;
 }
 
 template <bool STAGED>
-struct Rows {  // adjacency rows of one env: shared-memory copy (STAGED, explicit LDS) or global
-    const uint32_t *p;
-    uint32_t sp;  // shared-window address of the env's rows when STAGED
+struct Rows {  // adjacency rows of one env in the TILED layout (ge_common.cuh:adj_tiled): shared-memory copy (STAGED, explicit LDS) or global
+    const uint32_t *p;  // element (row 0, this env)
+    uint32_t sp;        // shared-window address of the same element when STAGED
     int NW;
     __device__ __forceinline__ u64 row(int r) const {
-        if (STAGED) {
+        if (STAGED) {   // rows of one tile are 32 elements apart: any 32 rows picked by the 32 lanes hit 32 different banks
             if (NW == 1) {
                 uint32_t v;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sp + 4u * (uint32_t)r));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sp + 128u * (uint32_t)r));
                 return (u64)v;
             }
             u64 v;
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sp + 8u * (uint32_t)r));
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sp + 256u * (uint32_t)r));
             return v;
         }
-        if (NW == 1) return (u64)__ldg(p + r);
-        uint2 t = __ldg(reinterpret_cast<const uint2 *>(p + 2 * r));
+        if (NW == 1) return (u64)__ldg(p + 32 * r);
+        uint2 t = __ldg(reinterpret_cast<const uint2 *>(p + 64 * r));
         return (u64)t.x | ((u64)t.y << 32);
     }
 };
@@ -87,7 +84,11 @@ struct Rows {  // adjacency rows of one env: shared-memory copy (STAGED, explici
 // so per-warp latency, not issue rate, is what a step waits for).  An empty slot re-expands the
 // seed, which is harmless.
 template <bool STAGED>
-__device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64 allowed) {
+__device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64 allowed, u64 need) {
+    // `need` (subset of allowed): the search may stop as soon as all of it is reached -- LongestPath only asks
+    // about the handful of candidates next to the head, which a well-connected residual graph reaches in one
+    // or two trips (reaching the LAST of ~45 allowed nodes took |allowed| / 8 trips).  need == allowed is the
+    // plain "everything reached" test.  On an empty frontier the returned set is the full component.
     const int sidx = __ffsll((long long)seed) - 1;
     u64 reach = seed, frontier = seed;
     while (frontier) {
@@ -103,7 +104,7 @@ __device__ __forceinline__ u64 reach_within(const Rows<STAGED> &R, u64 seed, u64
         u64 nx = a & allowed & ~reach;
         reach |= nx;
         frontier = rest | nx;
-        if (reach == allowed) break;
+        if (!(need & ~reach)) break;
     }
     return reach;
 }
@@ -129,7 +130,7 @@ __device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows<STAGED> &
 #ifdef GE_KNOBS
         if (d.flags & 0x100u) return m;
 #endif
-        m &= reach_within(R, 1ull << dest, allowed);
+        if (m) m &= reach_within(R, 1ull << dest, allowed, m);               // has_path(k, dest) for the candidates k (:137-140)
         if (d.parenting == 3 && __popcll(allowed) <= N / 3) m |= allowed;     // :141-143
         return m; }
     case GE_TSP: {                                                             // tsp.py:174-199
@@ -161,7 +162,7 @@ __device__ __forceinline__ u64 lane_mask(const ge_batch &d, const Rows<STAGED> &
             if (n_res - 1 == 0) break;                                         // :191-192
             u64 g = res & ~(1ull << v);
             u64 seed = g & (~g + 1ull);                                        // lowest node of G_copy
-            if (reach_within(R, seed, g) != g) m &= ~(1ull << v);              // :193-194
+            if (reach_within(R, seed, g, g) != g) m &= ~(1ull << v);           // :193-194
         }
         return m; }
     case GE_MAX_INDEPENDENT_SET: return ~s.vis & full;                         // max_independent_set.py:92-100
@@ -225,30 +226,29 @@ __device__ __forceinline__ u64 load_bits64(const uint32_t *base, int b, int NW) 
     return (u64)t.x | ((u64)t.y << 32);
 }
 
-// Stages the adjacency bit-matrices of the block's envs with one bulk copy; returns this env's rows.
+// Stages the adjacency tiles of the block's envs (blockDim.x / 32 tiles of 32 envs, contiguous) with one bulk
+// copy; returns this env's rows.
 template <bool STAGED>
 __device__ __forceinline__ Rows<STAGED> stage_rows(const ge_batch &d, int b0, uint32_t *smem, uint64_t *bar) {
     Rows<STAGED> R;
     R.NW = d.NW;
     R.sp = 0;
-    const int b = b0 + threadIdx.x;
-    if (!STAGED) {
-        R.p = d.adj_bits + (size_t)min(b, d.B - 1) * d.ADJS;
-        return R;
-    }
+    const int b = min(b0 + (int)threadIdx.x, d.B - 1);
+    const size_t tile_words = (size_t)d.N * 32 * d.NW;
+    R.p = d.adj_bits + (size_t)(b >> 5) * tile_words + (size_t)(b & 31) * d.NW;
+    if (!STAGED) return R;
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
 #ifdef GE_KNOBS
-    if (d.flags & 0x200u) { if (threadIdx.x == 0) mbar_expect_tx(bar, 0); R.p = smem + (size_t)threadIdx.x * d.ADJS; R.sp = smem_u32(R.p); return R; }
+    if (d.flags & 0x200u) { if (threadIdx.x == 0) mbar_expect_tx(bar, 0); R.sp = smem_u32(smem + (size_t)(threadIdx.x >> 5) * tile_words + (size_t)(threadIdx.x & 31) * d.NW); return R; }
 #endif
     if (threadIdx.x == 0) {
-        int nenv = min((int)blockDim.x, d.B - b0);
-        uint32_t bytes = ((uint32_t)nenv * (uint32_t)d.ADJS * 4u + 15u) & ~15u;  // adj_bits carries 16 B of slack
+        const int ntiles = (min((int)blockDim.x, d.B - b0) + 31) >> 5;     // adj_bits holds whole tiles (B rounded up to 32 envs)
+        const uint32_t bytes = (uint32_t)(ntiles * tile_words * 4);        // a multiple of 128
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem, d.adj_bits + (size_t)b0 * d.ADJS, bytes, bar);
+        bulk_g2s(smem, d.adj_bits + (size_t)(b0 >> 5) * tile_words, bytes, bar);
     }
-    R.p = smem + (size_t)threadIdx.x * d.ADJS;
-    R.sp = smem_u32(R.p);
+    R.sp = smem_u32(smem + (size_t)(threadIdx.x >> 5) * tile_words + (size_t)(threadIdx.x & 31) * d.NW);
     return R;
 }
 
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
         }
         was_done = d.done[b] != 0;
         if (kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH) { dest = d.dest[b]; src = d.src[b]; }
-        acc_r = d.acc[2 * (size_t)d.B + b];
+        acc_r = d.acc[2 * (size_t)d.acc_stride + b];
         if (d.mask0_bits && (d.flags & GE_FLAG_AUTO_RESET)) mask0 = load_bits64(d.mask0_bits, b, d.AW);
         if (d.traj) cs = d.traj[b];
         // the one dependent load of the step, issued before waiting for the staged rows
@@ -400,11 +400,11 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
         d.traj[b] = ((cs << 7) | (cs >> 57)) ^ (u64)(uint32_t)a ^ ((u64)done << 40) ^ ((u64)(solved & 3) << 44) ^ ((u64)status << 48);
     if (status == GE_STEP_OK) {
         if (d.env_steps) d.env_steps[b] = nsteps + 1u;
-        d.acc[2 * (size_t)d.B + b] = acc_r + reward;
+        d.acc[2 * (size_t)d.acc_stride + b] = acc_r + reward;
         if (done) {
             d.acc[b] += 1.0;
-            if (solved == 1) d.acc[(size_t)d.B + b] += 1.0;
-            if (sol == sol) d.acc[3 * (size_t)d.B + b] += sol;
+            if (solved == 1) d.acc[(size_t)d.acc_stride + b] += 1.0;
+            if (sol == sol) d.acc[3 * (size_t)d.acc_stride + b] += sol;
         }
     }
     if (done && (d.flags & GE_FLAG_AUTO_RESET)) {                               // tail of reset()
@@ -476,7 +476,7 @@ static int lane_threads(const ge_batch *d) {
     if (forced) return forced;
     return 64;
 }
-static size_t lane_smem(const ge_batch *d, int T) { return lane_stages(*d) ? (size_t)T * d->ADJS * 4 + 16 : 0; }
+static size_t lane_smem(const ge_batch *d, int T) { return lane_stages(*d) ? (size_t)T * d->N * d->NW * 4 : 0; }
 
 int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 template <class K>

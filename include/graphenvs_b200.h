@@ -6,7 +6,9 @@
  * library allocates nothing and keeps no state between calls, so a descriptor can be copied,
  * sliced per rank, or rebuilt freely.  All calls enqueue work on `stream` (a cudaStream_t passed
  * as void*), return 0 on success / a negative ge_status on error (text via ge_last_error()),
- * never throw, and are not thread-safe per descriptor.  No torch types appear here.
+ * never throw, and are not thread-safe per descriptor (two host threads may work on DIFFERENT descriptors
+ * concurrently: the library's only process-wide state, its kernel-attribute table and its CUDA-graph cache,
+ * is mutex-guarded).  No torch types appear here.
  *
  * What each entry point replaces in the reference (paths relative to graph_envs/):
  *   ge_reset          tail of every Env.reset(): state init + first info['mask']
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define GE_ABI_VERSION 1
+#define GE_ABI_VERSION 2
 
 typedef enum {
     GE_SHORTEST_PATH = 0,      /* ShortestPath-v0        shortest_path.py        node actions */
@@ -89,6 +91,9 @@ typedef struct ge_batch {
     int32_t NW, MW;               /* ceil(N/32), ceil(M/32) */
     int32_t A, AW, AP;            /* mask length (N or M), its words, byte stride (A rounded up to 16) */
     int32_t RP, MP, ADJS;         /* strides: row_ptr (ints), col/w (elements), adj_bits (words) per env */
+    int32_t acc_stride;           /* elements between the 4 components of `acc` (= B of the batch the array was allocated for;
+                                     ge_fill_layout sets it to B, ge_batch_slice keeps the parent's) */
+    int32_t reserved0;
     double max_distance;          /* DistributionCenter cutoff */
 
     /* ---- graph store (static per instance) ---- */
@@ -96,7 +101,10 @@ typedef struct ge_batch {
     const int32_t *col;           /* [B, MP]   destination of every directed edge */
     const float *w32;             /* [B, MP]   edge feature column 0 (float32), kinds stepping in fp32 */
     const double *w64;            /* [B, MP]   float64 edge attribute, kinds stepping in fp64 / prepare */
-    uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived); allocate 16 B of slack */
+    uint32_t *adj_bits;           /* [B, ADJS] N rows of NW words: adjacency bit-matrix (derived by ge_build_adjacency).
+                                              For N <= 64 node-action kinds without GE_FLAG_FORCE_WARP the library stores it in
+                                              tiles of 32 envs, [ceil(B/32)][N][32 envs] of NW words (bank-conflict-free for the
+                                              lane-per-env kernels): allocate (B rounded up to 32) * ADJS words */
     int32_t *rev;                 /* [B, MP]   index of the reverse edge (v->u) of every edge (u->v) (derived), or NULL */
     int32_t *esrc;                /* [B, MP]   source node of every edge (derived), or NULL */
     double *wsort;                /* [B, MP]   w64 permuted so that every row is in ascending destination order (derived), or
@@ -143,7 +151,7 @@ typedef struct ge_batch {
                                               the whole mask, not by the incremental ones (ge_mask_mirror_supported) */
     uint32_t *mask0_bits;         /* [B, AW]  mask right after reset(), written by ge_reset, or NULL.  It depends only on the
                                               instance, so auto-reset inside ge_step copies it instead of recomputing it */
-    double *acc;                  /* [4, B]   per-env statistics: episodes, solved, sum reward, sum final cost */
+    double *acc;                  /* [4, acc_stride] per-env statistics: episodes, solved, sum reward, sum final cost */
     uint64_t *traj;               /* [B]      rolling checksum of (action, done, solved, status) per env, or NULL;
                                               same recurrence as oracle/graphenvs_oracle.c oenv_rollout */
     uint32_t *env_steps;          /* [B]      per-env count of accepted steps, or NULL.  ge_step increments it and the
@@ -163,18 +171,27 @@ const char *ge_last_error(void);
 
 /* Fills the derived size fields (NW, MW, A, AW, AP, RP, MP, ADJS) from kind/N/M. */
 int ge_fill_layout(ge_batch *batch);
+/* Descriptor of the sub-batch [lo, lo + count) of `batch`: every per-env pointer advanced, B = count, env_id0 += lo.
+ * All arrays are SoA with fixed per-env strides, so a slice is a contiguous range of each of them; it can be stepped,
+ * reset and observed on its own (other streams, other host threads).  `lo` must be a multiple of 32. */
+int ge_batch_slice(const ge_batch *batch, int lo, int count, ge_batch *out);
 /* Bytes of dynamic shared memory one step launch uses (for diagnostics / occupancy reports). */
 int ge_step_smem_bytes(const ge_batch *batch);
 
 /* Fills every DERIVED graph array whose pointer is set: adj_bits, wmat, wsort, rev, esrc, wmin. */
 int ge_build_adjacency(const ge_batch *batch, void *stream);
 /* what: bit0 heuristics (SSSP / MST where the reference's value is tie-independent),
- *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw),
- *       bit2 DistributionCenter in-range tables.  u01 may be NULL unless bit1 is set. */
+ *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw); u01 == NULL takes the draw
+ *            ge_generate left in max_dist32 (a pure function of seed and global env id),
+ *       bit2 DistributionCenter in-range tables. */
 int ge_prepare(const ge_batch *batch, int what, const double *u01, void *stream);
 int ge_features(const ge_batch *batch, void *stream);
 int ge_generate(const ge_batch *batch, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32,
                 void *stream);
+
+/* Envs of the most recent ge_generate on `stream` whose rejection loop (4096 draws) found no valid graph and that were
+ * emitted connected-by-construction instead; synchronises the stream.  Negative = error. */
+int ge_generate_fallbacks(void *stream);
 
 /* select: device uint8[B] (1 = reset this env) or NULL for all. */
 int ge_reset(const ge_batch *batch, const uint8_t *select, void *stream);
@@ -190,6 +207,10 @@ int ge_obs_flat(const ge_batch *batch, int env_lo, int count, float *out, void *
 /* The same observation as three tensors (what utils.devectorize_graph, utils.py:14-23, slices out of the flat vector):
  * x float32[count, N, F], edge_attr float32[count, M, Fe], edge_index int64[count, M, 2] -- no float round trip of indices. */
 int ge_obs_graph(const ge_batch *batch, int env_lo, int count, float *x, float *edge_attr, int64_t *edge_index, void *stream);
+/* x only: the node columns are the part of the observation a step changes (utils.py:14-23 `x`). */
+int ge_obs_nodes(const ge_batch *batch, int env_lo, int count, float *x, void *stream);
+/* Name of the CUDA kernel ge_step / ge_step_sampled dispatches this descriptor to (reports, profiles). */
+const char *ge_step_kernel_name(const ge_batch *batch, int sampled);
 
 /* End-to-end entry with HOST buffers: copies actions H2D, steps, copies reward / flags /
  * solution_cost (and the byte mask [B, AP] when h_mask != NULL, the packed mask [B, AW] when
@@ -205,6 +226,17 @@ int ge_mask_mirror_supported(const ge_batch *batch);
 int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                  float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
                  uint32_t *h_mask_bits, void *stream);
+
+/* PIPELINED end-to-end step with pinned (device-mapped) HOST buffers.  The batch is cut into `chunks` slices; each slice
+ * runs copy-in -> step kernel -> write-back on its own branch of ONE CUDA graph, so slice i's results cross PCIe while
+ * slice i+1 is stepping and slice i+2's actions arrive.  Results are written back by a small copy kernel straight into
+ * the caller's four host arrays (coalesced 128-byte PCIe writes; no staging layout imposed on the host side).  Blocks
+ * until the results are visible to the host (spin on stream completion).  h_solution_cost / h_mask_bits may be NULL. */
+int ge_step_host_pipelined(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
+                           float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits,
+                           int chunks, void *stream);
+/* Drops the cached CUDA graphs ge_step_host / ge_step_host_pipelined built for this batch (call before freeing its memory). */
+int ge_step_host_release(const ge_batch *batch);
 
 /* Reduces acc[4,B] to out[4] (device double[4]): episodes, solved, sum reward, sum final cost. */
 int ge_stats(const ge_batch *batch, double *out4, void *stream);

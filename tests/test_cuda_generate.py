@@ -107,3 +107,157 @@ def test_rank_sliced_generation_equals_single_batch():
         a = full.t[name]
         b = torch.cat([h.t[name] for h in halves], dim=1 if name == "acc" else 0)
         assert torch.equal(a, b), name
+
+
+def test_rank_sliced_multicast_generation_equals_single_batch():
+    """the Multicast max_distance uniform must be a function of the GLOBAL env id, not of the rank's batch."""
+    kw = dict(n_dests=4, parenting=4)
+    full = BatchedGraphEnv("MulticastRouting-v0", 96, 60, 200, auto_reset=True, **kw)
+    full.generate(seed=9)
+    full.reset()
+    parts = []
+    for r in range(3):
+        h = BatchedGraphEnv("MulticastRouting-v0", 32, 60, 200, auto_reset=True, env_id0=32 * r, **kw)
+        h.generate(seed=9)
+        h.reset()
+        parts.append(h)
+    for t in range(30):
+        for e in [full] + parts:
+            e.sample_actions(77, t)
+            e.step_async(e.actions_dev)
+    torch.cuda.synchronize()
+    md = full.t["max_dist32"]
+    assert len(torch.unique(md)) > 48, "per-env draws"
+    for name in ("row_ptr", "col", "w32", "max_dist32", "target_bits", "node_bits", "mask_bits", "dist32", "cost", "acc", "traj"):
+        a = full.t[name]
+        b = torch.cat([h.t[name] for h in parts], dim=1 if name == "acc" else 0)
+        assert torch.equal(a, b), name
+
+
+def _edge_order_is_consistent(links, N):
+    """True iff ONE order of the undirected edges explains every row: row u lists its neighbours in the order the edges
+    touching u were inserted (list(G.to_directed().edges) of the reference).  Kahn's algorithm over the constraints
+    'edge of row slot i precedes edge of row slot i+1'."""
+    from collections import defaultdict, deque
+    rows = defaultdict(list)
+    for u, v in links.tolist():
+        rows[u].append((min(u, v), max(u, v)))
+    succ, indeg = defaultdict(list), defaultdict(int)
+    nodes = set()
+    for u, es in rows.items():
+        nodes.update(es)
+        for a, b in zip(es[:-1], es[1:]):
+            succ[a].append(b)
+            indeg[b] += 1
+    q = deque(e for e in nodes if indeg[e] == 0)
+    seen = 0
+    while q:
+        e = q.popleft()
+        seen += 1
+        for f in succ[e]:
+            indeg[f] -= 1
+            if indeg[f] == 0:
+                q.append(f)
+    return seen == len(nodes)
+
+
+def test_rows_are_in_insertion_order_like_the_reference():
+    """rows were neighbour-sorted; the reference's are insertion-ordered (decides np.argmin ties under
+    Multicast parenting >= 3).  The device rows must be explainable by one global edge order, and must NOT be sorted."""
+    import random
+    from graphenvs_b200.instances import generate_instance
+    env = BatchedGraphEnv("MulticastRouting-v0", 64, 120, 600, n_dests=5, parenting=4)
+    env.generate(seed=2)
+    torch.cuda.synchronize()
+    unsorted_rows = total_rows = 0
+    for ins in env.export_instances():
+        assert _edge_order_is_consistent(ins.links, 120)
+        rp = np.searchsorted(ins.links[:, 0], np.arange(121))
+        for u in range(120):
+            r = ins.links[rp[u]:rp[u + 1], 1]
+            total_rows += 1
+            unsorted_rows += int(np.any(r[1:] < r[:-1]))
+    assert unsorted_rows > 0.8 * total_rows, "rows look sorted: %d of %d unsorted" % (unsorted_rows, total_rows)
+    # the host generator (= the reference's draws) passes the same consistency check, i.e. the check is the right one
+    random.seed(1); np.random.seed(1)
+    ref = generate_instance("MulticastRouting-v0", env.params)
+    assert _edge_order_is_consistent(ref.links, 120)
+
+
+def test_generated_distribution_matches_host_generator():
+    """Distribution parity with the reference's reset(): degree histogram, position of a neighbour id inside its row
+    (uniform for insertion order), terminal uniformity -- device generator vs the host generator that replays the
+    reference's own draws."""
+    import random
+    from graphenvs_b200.instances import generate_instance
+    env_id, N, E, kw = "SteinerTree-v0", 40, 100, {"n_dests": 4}
+    B = 2048
+    env = BatchedGraphEnv(env_id, B, N, E, **kw)
+    env.generate(seed=17)
+    torch.cuda.synchronize()
+    rp = env.t["row_ptr"][:, :N + 1].cpu().numpy()
+    deg_dev = np.bincount(np.diff(rp, axis=1).ravel(), minlength=24)[:24] / (B * N)
+    tb = env.t["target_bits"].cpu().numpy().view(np.uint32)
+    tgt = np.unpackbits(tb.view(np.uint8), axis=1, bitorder="little")[:, :N].sum(0) / B
+    src = np.bincount(env.t["src"].cpu().numpy(), minlength=N) / B
+    deg_host = np.zeros(24)
+    H = 300
+    for b in range(H):
+        random.seed(500 + b); np.random.seed(500 + b)
+        ins = generate_instance(env_id, env.params)
+        deg_host += np.bincount(np.bincount(ins.links[:, 0], minlength=N), minlength=24)[:24]
+    deg_host /= H * N
+    assert np.abs(deg_dev - deg_host).max() < 0.02, (deg_dev, deg_host)
+    assert np.abs(tgt - kw["n_dests"] / N).max() < 0.03 and np.abs(src - 1 / N).max() < 0.02
+    # first slot of a row: under insertion order the smallest neighbour id is first only ~1/deg of the time
+    col = env.t["col"].cpu().numpy()
+    first_is_min = 0
+    rows = 0
+    for b in range(256):
+        for u in range(N):
+            r = col[b, rp[b, u]:rp[b, u + 1]]
+            if r.size >= 3:
+                rows += 1
+                first_is_min += int(r[0] == r.min())
+    assert first_is_min / rows < 0.45
+
+
+def test_sparse_configuration_falls_back_to_connected_by_construction():
+    """when 4096 rejection draws find no valid graph (a tree-sparse G(n, n-1) is almost never connected) the
+    generator used to emit the last rejected graph.  Now every env is valid and the fallbacks are counted."""
+    import warnings
+    for env_id, N, E, kw in [("SteinerTree-v0", 60, 59, {"n_dests": 3}), ("TSP-v0", 40, 41, {"parenting": 1})]:
+        env = BatchedGraphEnv(env_id, 32, N, E, auto_reset=True, **kw)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            env.generate(seed=3)
+        assert env.generate_fallbacks > 0 and any("connected-by-construction" in str(x.message) for x in w)
+        for ins in env.export_instances():
+            adj = [[] for _ in range(N)]
+            for u, v in ins.links:
+                adj[u].append(v)
+            assert len(set(map(tuple, ins.links.tolist()))) == 2 * E
+            assert _connected(adj, range(N))
+            if env_id == "TSP-v0":
+                assert min(len(a) for a in adj) >= 2 and _connected(adj, range(1, N))
+        env.reset()
+        for t in range(20):          # the envs step and finish episodes
+            env.step_sampled(1, t)
+        torch.cuda.synchronize()
+        assert int(env.flags[:, 2].max()) == 0
+    ok = BatchedGraphEnv("LongestPath-v0", 256, 50, 200, parenting=2)
+    ok.generate(seed=3)
+    assert ok.generate_fallbacks == 0
+
+
+def test_spatial_tsp_generation_is_euclidean():
+    """spatial=True got zero coordinates and k/10 weights; tsp.py:80-86 draws U(0,10)^2 and uses distances."""
+    env = BatchedGraphEnv("TSP-v0", 16, 30, 80, parenting=1, spatial=True)
+    env.generate(seed=4)
+    torch.cuda.synchronize()
+    xy = env.t["node_xy"].cpu().numpy().astype(np.float64)
+    assert xy.min() >= 0 and xy.max() <= 10 and xy.std() > 2
+    for b, ins in enumerate(env.export_instances()):
+        u, v = ins.links[:, 0], ins.links[:, 1]
+        dist = np.sqrt(((xy[b, u] - xy[b, v]) ** 2).sum(1))
+        np.testing.assert_allclose(ins.w64, dist, rtol=1e-5)     # xy is stored as float32, the weight came from fp64 coordinates

@@ -49,6 +49,8 @@ CONFIGS = [
     ("TSP-v0", 40, 120, {"parenting": 1}, 50),
     ("TSP-v0", 40, 120, {"parenting": 2}, 50),
     ("TSP-v0", 70, 2415, {"parenting": 2}, 80),               # complete graph, N > 64
+    ("TSP-v0", 200, 600, {"parenting": 2}, 220),              # SPARSE N > 64: the cut-vertex pruning is not vacuous
+    ("DensestSubgraph-v0", 500, 4000, {"parenting": 1}, 60),  # the bench's Densest shape
     ("MaxIndependentSet-v0", 200, 600, {}, 210),
     ("DensestSubgraph-v0", 80, 300, {"parenting": 1}, 40),
     ("DensestSubgraph-v0", 80, 300, {"parenting": 0}, 40),
@@ -242,3 +244,80 @@ def test_obs_graph_equals_devectorized_flat_obs(cfg):
     x, ea, ei = env.obs_graph(3, 20)
     fx, fe, fi = utils.devectorize_graph(flat, env_id, n_nodes=N, n_edges=E)
     assert torch.equal(x, fx) and torch.equal(ea, fe) and torch.equal(ei, fi) and ei.dtype == torch.int64
+
+
+@pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}), ("TSP-v0", 100, 400, {"parenting": 2}),
+                                 ("SteinerTree-v0", 60, 150, {"n_dests": 5}), ("MulticastRouting-v0", 60, 200, {"parenting": 4, "n_dests": 3}),
+                                 ("DistributionCenter-v0", 90, 300, {"parenting": 2}), ("MaxIndependentSet-v0", 200, 600, {})],
+                         ids=lambda c: c[0][:-3])
+def test_pipelined_host_step_equals_single_pass(cfg):
+    """ge_step_host_pipelined (slices on parallel graph branches, kernel-driven write-back into the four pinned host
+    arrays) returns what ge_step_host returns, step after step, for every kernel family; B is not a multiple of the
+    slice size, so the last slice is ragged."""
+    env_id, N, E, kw = cfg
+    B, T = 1000, 30
+    logs = []
+    for pipelined in (False, True):
+        e = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+        e.generate(seed=33)
+        e.reset()
+        blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
+        h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
+        side = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3)
+        log = []
+        for t in range(T):
+            h_act.copy_(e.sample_actions(9, t).cpu())
+            torch.cuda.synchronize()
+            stepper()
+            assert torch.equal(h_bits, e.t["mask_bits"].cpu()), "host mask must equal the device mask after the call"
+            assert torch.equal(h_rew, e.reward.cpu()) and torch.equal(h_flg, e.flags.cpu())
+            log.append((h_rew.clone(), h_flg.clone(), h_cost.clone(), h_bits.clone()))
+        logs.append((log, e.t["traj"].clone(), e.t["acc"].clone()))
+        del stepper
+    (l0, t0, a0), (l1, t1, a1) = logs
+    for (r0, f0, c0, m0), (r1, f1, c1, m1) in zip(l0, l1):
+        assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
+        assert torch.equal(torch.nan_to_num(c0, nan=-7.0), torch.nan_to_num(c1, nan=-7.0))
+    assert torch.equal(t0, t1) and torch.equal(a0, a1)
+
+
+def test_sliced_descriptors_step_like_the_full_batch():
+    """ge_batch_slice: stepping the three slices of a batch one after the other == stepping the batch (same memory)."""
+    import ctypes as C
+    from graphenvs_b200 import _native
+    for env_id, N, E, kw in [("LongestPath-v0", 50, 200, {"parenting": 2}), ("MulticastRouting-v0", 60, 200, {"parenting": 4, "n_dests": 3})]:
+        B, T = 700, 25
+        full = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+        part = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
+        for e in (full, part):
+            e.generate(seed=5)
+            e.reset()
+        cuts = [(0, 256), (256, 320), (576, 124)]
+        descs = [part.slice_desc(lo, n) for lo, n in cuts]
+        for t in range(T):
+            acts = full.sample_actions(4, t).clone()
+            full.step_async(acts)
+            for (lo, n), dsc in zip(cuts, descs):
+                out = _native.StepOut(part.reward[lo:].data_ptr(), part.flags[lo:].data_ptr(), part.solution_cost[lo:].data_ptr())
+                _native.check(part.lib.ge_step(C.byref(dsc), acts[lo:].data_ptr(), C.byref(out), part._stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(full.reward, part.reward) and torch.equal(full.flags, part.flags)
+        for name in ("traj", "acc", "mask_bits", "node_bits", "cost"):
+            assert torch.equal(full.t[name], part.t[name]), name
+
+
+def test_obs_nodes_is_the_x_tensor_of_obs_graph():
+    for env_id, N, E, kw in [("LongestPath-v0", 50, 200, {"parenting": 2}), ("DistributionCenter-v0", 90, 300, {"parenting": 2}),
+                             ("MulticastRouting-v0", 60, 200, {"parenting": 4, "n_dests": 3}), ("TSP-v0", 33, 100, {"parenting": 1})]:
+        env = BatchedGraphEnv(env_id, 50, N, E, auto_reset=True, structural_features=True, **kw)
+        env.generate(seed=8)
+        env.reset()
+        for t in range(5):
+            env.step_sampled(2, t)
+        x, ea, ei = env.obs_graph()
+        assert torch.equal(env.obs_nodes(), x)
+        assert torch.equal(env.obs_nodes(7, 11), x[7:18])
+        name = env.step_kernel_name(sampled=True)
+        assert name.endswith(">") and "step_kernel<" in name

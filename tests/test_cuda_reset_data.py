@@ -55,8 +55,13 @@ def test_features_large_vs_oracle():
     import random
     from graphenvs_b200.instances import generate_instance
     for env_id, N, E, kw in [("ShortestPath-v0", 150, 400, {}), ("TSP-v0", 60, 400, {"parenting": 1}),
-                             ("MaxIndependentSet-v0", 200, 5970, {}), ("DensestSubgraph-v0", 90, 300, {"parenting": 1})]:
-        B = 6
+                             ("MaxIndependentSet-v0", 200, 5970, {}), ("DensestSubgraph-v0", 90, 300, {"parenting": 1}),
+                             ("TSP-v0", 200, 19900, {"parenting": 1}),               # config 4: complete graph, weighted pagerank
+                             ("MulticastRouting-v0", 500, 4000, {"parenting": 4}),   # config 5 graph size (16 set words)
+                             ("ShortestPath-v0", 1000, 2500, {}),                     # 32 set words, long BFS levels
+                             ("ShortestPath-v0", 1100, 3000, {}),                     # N > 1024: the warp-per-env kernel
+                             ("ShortestPath-v0", 9, 12, {}), ("DensestSubgraph-v0", 40, 45, {"parenting": 0})]:   # near-trees: deep levels
+        B = 6 if N < 500 else 3
         env = BatchedGraphEnv(env_id, B, N, E, structural_features=True, **kw)
         inst = []
         for b in range(B):
@@ -95,3 +100,23 @@ def test_device_heuristics_match_reference_values_beyond_fixture_sizes():
         got = env.t["heuristic"].cpu().numpy()
         for b, h in enumerate(lst):
             assert got[b] == pytest.approx(h["heuristic"], rel=1e-9), (env_id, kw, h["seed"])
+
+
+def test_features_cta_kernel_equals_warp_kernel():
+    """Round-2 CTA-per-env features kernel vs the round-1 warp-per-env kernel (force_warp): same float32 columns up to
+    fp64 reassociation."""
+    import random
+    from graphenvs_b200.instances import generate_instance
+    for env_id, N, E, kw in [("LongestPath-v0", 50, 200, {"parenting": 2}), ("SteinerTree-v0", 100, 500, {"n_dests": 99}),
+                             ("DistributionCenter-v0", 300, 1200, {"parenting": 2})]:
+        inst = []
+        for b in range(16):
+            random.seed(90 + b); np.random.seed(90 + b)
+            inst.append(generate_instance(env_id, BatchedGraphEnv(env_id, 1, N, E, **kw).params))
+        got = []
+        for fw in (False, True):
+            env = BatchedGraphEnv(env_id, 16, N, E, structural_features=True, force_warp=fw, **kw)
+            env.load_instances(inst)
+            torch.cuda.synchronize()
+            got.append(env.t["features"].cpu().numpy())
+        np.testing.assert_allclose(got[0], got[1], rtol=1e-6, atol=1e-9, err_msg=env_id)

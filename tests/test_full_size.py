@@ -32,8 +32,7 @@ def _oracle_slice_matches(env, env_id, T, n=192, lo=0):
     np.testing.assert_allclose(acc[2], sr, rtol=1e-5, atol=1e-4)
     masks = np.stack([oe.mask(reset_patch=False) for oe in oenvs])
     got = env.mask[lo:lo + n].cpu().numpy()
-    if env_id != "TSP-v0":
-        np.testing.assert_array_equal(got, masks)
+    np.testing.assert_array_equal(got, masks)
 
 
 def test_cfg2_longest_path_65536():
@@ -46,7 +45,7 @@ def test_cfg2_longest_path_65536():
     _oracle_slice_matches(env, "LongestPath-v0", T, n=64, lo=B - 64)
     nb, mb, head = env.t["node_bits"], env.t["mask_bits"], env.t["head"].long()
     assert not (nb & mb).any(), "a visited node is offered as an action"
-    adj = env.t["adj_bits"][:, :50 * 2].view(B, 50, 2)
+    adj = env.adjacency_rows()
     rows = adj[torch.arange(B, device=adj.device), head]
     assert not (mb & ~rows).any(), "mask must be a subset of N(head)"
     acc = env.t["acc"]
@@ -120,6 +119,8 @@ def _oracle_slice_matches_tsp(tsp, T):
     sr, ep, cs = orc.rollout(oenvs, T, SEED)
     np.testing.assert_array_equal(tsp.t["traj"][:24].cpu().numpy().view(np.uint64), cs)
     np.testing.assert_allclose(tsp.t["acc"][2, :24].cpu().numpy(), sr, rtol=1e-5)
+    masks = np.stack([oe.mask(reset_patch=False) for oe in oenvs])
+    np.testing.assert_array_equal(tsp.mask[:24].cpu().numpy(), masks)
 
 
 def test_cfg4_tsp_parenting2_slice():
@@ -136,21 +137,29 @@ def test_cfg4_tsp_parenting2_slice():
     oenvs = [cu.oracle_from_instance("TSP-v0", i, tsp.params) for i in inst]
     sr, ep, cs = orc.rollout(oenvs, N, SEED)
     np.testing.assert_array_equal(tsp.t["traj"][:4].cpu().numpy().view(np.uint64), cs)
+    np.testing.assert_array_equal(tsp.mask[:4].cpu().numpy(), np.stack([oe.mask(reset_patch=False) for oe in oenvs]))
+    # mid-episode masks too (the tour above has ended): 60 moves into a fresh episode
+    tsp.reset()
+    _rollout(tsp, 60)
+    oenvs = [cu.oracle_from_instance("TSP-v0", i, tsp.params) for i in inst]
+    orc.rollout(oenvs, 60, SEED)
+    np.testing.assert_array_equal(tsp.mask[:4].cpu().numpy(), np.stack([oe.mask(reset_patch=False) for oe in oenvs]))
 
 
 def test_cfg5_multicast_and_distcenter_large():
     N, E = 500, 4000
-    B = 16384   # per-GPU share of config 5 at 8 GPUs is 65,536 per env kind; kept smaller to bound test time
+    B = 131072   # the batch bench.py steps per GPU; 256-env oracle slices from the start, the middle and the end
     mc = BatchedGraphEnv("MulticastRouting-v0", B, N, E, n_dests=3, parenting=4, auto_reset=True)
     mc.generate(seed=6)
     mc.reset()
-    T = 40
+    T = 24
     _rollout(mc, T)
-    _oracle_slice_matches(mc, "MulticastRouting-v0", T, n=24)
+    for lo in (0, B // 2 - 128, B - 256):
+        _oracle_slice_matches(mc, "MulticastRouting-v0", T, n=256, lo=lo)
     # parenting 4 keeps exactly one candidate edge per frontier vertex
-    mb = mc.t["mask_bits"].cpu().numpy().view(np.uint32)
-    col = mc.t["col"].cpu().numpy()
-    bits = np.unpackbits(mb[:64].view(np.uint8), axis=1, bitorder="little")[:, :2 * E].astype(bool)
+    mb = mc.t["mask_bits"][:64].cpu().numpy().view(np.uint32)
+    col = mc.t["col"][:64].cpu().numpy()
+    bits = np.unpackbits(mb.view(np.uint8), axis=1, bitorder="little")[:, :2 * E].astype(bool)
     for b in range(64):
         dst = col[b, :2 * E][bits[b]]
         assert len(set(dst.tolist())) == dst.size, "two candidate edges for one frontier vertex"
@@ -158,8 +167,11 @@ def test_cfg5_multicast_and_distcenter_large():
     dc = BatchedGraphEnv("DistributionCenter-v0", B, N, E, parenting=2, target_count=100, max_distance=1, auto_reset=True)
     dc.generate(seed=7)
     dc.reset()
+    del mc
+    torch.cuda.empty_cache()
     _rollout(dc, 30)
-    _oracle_slice_matches(dc, "DistributionCenter-v0", 30, n=16)
+    for lo in (0, B // 2 - 128, B - 256):
+        _oracle_slice_matches(dc, "DistributionCenter-v0", 30, n=256, lo=lo)
     taken, covered, mask = dc.t["node_bits"], dc.t["node_bits2"], dc.t["mask_bits"]
     assert not (taken & mask).any()
     assert ((taken & covered) == taken).all(), "a chosen centre covers itself"
