@@ -84,7 +84,7 @@ class GeBatch(C.Structure):
         ("max_distance", C.c_double),
         ("row_ptr", _P), ("col", _P), ("w32", _P), ("w64", _P), ("adj_bits", _P), ("rev", _P), ("esrc", _P), ("wsort", _P), ("wcode", _P), ("dfa", _P), ("wmin", _P), ("wmat", _P),
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
-        ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("features", _P),
+        ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("heuristic_alt", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P), ("bestkey", _P),
         ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_bytes", _P), ("mask_mirror", _P), ("mask0_bits", _P), ("acc", _P), ("traj", _P), ("env_steps", _P),
     ]
@@ -97,7 +97,7 @@ class StepOut(C.Structure):
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
            "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
            "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined",
-           "ge_step_host_release", "ge_mask_mirror_supported", "ge_stats"]
+           "ge_step_host_release", "ge_mask_mirror_supported", "ge_mask_bytes_current", "ge_mask_bytes", "ge_stats"]
 
 _lib = None
 
@@ -141,6 +141,8 @@ def lib():
     L.ge_batch_slice.argtypes = [BP, C.c_int, C.c_int, BP]
     L.ge_stats.argtypes = [BP, _P, _P]
     L.ge_mask_mirror_supported.argtypes = [BP]
+    L.ge_mask_bytes_current.argtypes = [BP]
+    L.ge_mask_bytes.argtypes = [BP, C.c_int, C.c_int, _P]
     if L.ge_abi_version() != 2:
         raise NativeError("ABI version mismatch")
     _lib = L

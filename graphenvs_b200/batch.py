@@ -14,7 +14,7 @@ import torch
 from . import _native
 from .spec import ENV_SPECS, check_ctor_args
 
-PREP_HEURISTIC, PREP_MAXDIST, PREP_INRANGE = 1, 2, 4
+PREP_HEURISTIC, PREP_MAXDIST, PREP_INRANGE, PREP_ALT_HEURISTIC = 1, 2, 4, 8
 
 
 def _ptr(t):
@@ -74,7 +74,7 @@ class BatchedGraphEnv:
         if not force_warp:   # derived / state arrays of the incremental-mask kernels (csrc/ge_incr.cu)
             if env_id == "SteinerTree-v0" or (env_id == "MulticastRouting-v0" and par == 2):
                 T["rev"] = z((B, d.MP), torch.int32)
-            if env_id == "MulticastRouting-v0" and par >= 2:
+            if env_id == "MulticastRouting-v0" and par == 2:
                 T["esrc"] = z((B, d.MP), torch.int32)
             if env_id == "MulticastRouting-v0" and par >= 3:
                 T["bestkey"] = z((B, N), torch.int64)
@@ -96,6 +96,11 @@ class BatchedGraphEnv:
             T["targets"] = z((B, max(d.n_targets, 1)), torch.int32)
             T["in_range"] = z((B, max(d.n_targets, 1), d.NW), torch.int32)
         T["heuristic"] = z((B,), torch.float64)
+        self.heuristic_device_name = None
+        if self.is_eval_env:
+            self.heuristic_device_name = self.spec.heuristic_alternative(P)
+            if self.heuristic_device_name:
+                T["heuristic_alt"] = z((B,), torch.float64)
         if self.structural_features:
             T["features"] = z((B, N, 5), torch.float32)
         T["head"] = z((B,), torch.int32)
@@ -130,7 +135,7 @@ class BatchedGraphEnv:
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
         for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
-                     "max_dist32", "targets", "in_range", "heuristic", "features", "head", "node_bits", "node_bits2",
+                     "max_dist32", "targets", "in_range", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
@@ -245,6 +250,8 @@ class BatchedGraphEnv:
             what |= PREP_INRANGE
         if heuristics and self.spec.heuristic_on_device(self.params):
             what |= PREP_HEURISTIC
+        if self.is_eval_env and "heuristic_alt" in self.t and ("w64" in self.t or self.env_id == "MaxIndependentSet-v0"):
+            what |= PREP_ALT_HEURISTIC
         if (u01 is not None or maxdist_from_generator) and self.env_id == "MulticastRouting-v0":
             what |= PREP_MAXDIST
         if what:
@@ -478,6 +485,9 @@ class BatchedGraphEnv:
 
     def info(self, step=False):
         d = {"mask": self.mask, "mask_bits": self.t["mask_bits"], "heuristic_solution": self.t["heuristic"]}
+        if self.heuristic_device_name:      # labelled alternative (Kou / Christofides / Ramsey are defined by networkx's iteration order)
+            d["heuristic_device"] = self.t["heuristic_alt"]
+            d["heuristic_device_name"] = self.heuristic_device_name
         if step:
             f = self.flags
             d.update(solved=f[:, 1].view(torch.int8), status=f[:, 2], has_mask=f[:, 3].bool(),
@@ -486,9 +496,15 @@ class BatchedGraphEnv:
 
     @property
     def mask(self):
-        """bool[B, A] view of the current valid-action masks (None when byte_mask=False)."""
+        """bool[B, A] view of the current valid-action masks (None when byte_mask=False).  For the incremental-mask kinds
+        (SteinerTree, Multicast parenting >= 2, MaxIndependentSet N > 64) the step kernels keep only the packed mask
+        current and this property expands it into the byte view first (ge_mask_bytes, one coalesced pass)."""
         mb = self.t.get("mask_bytes")
-        return None if mb is None else mb[:, :self.desc.A].view(torch.bool)
+        if mb is None:
+            return None
+        if not self.lib.ge_mask_bytes_current(C.byref(self.desc)):
+            _native.check(self.lib.ge_mask_bytes(C.byref(self.desc), 0, self.B, self._stream()))
+        return mb[:, :self.desc.A].view(torch.bool)
 
     def obs_flat(self, env_lo=0, count=None):
         """Reference wire format (utils.vectorize_graph): float32[count, obs_len]."""

@@ -405,6 +405,18 @@ __global__ void __launch_bounds__(GE_WPB * 32) prep_inrange_kernel(ge_batch d, i
     for (int w = lane; w < d.NW; w += 32) row[w] = s.t2[w];
 }
 
+// Packed mask -> byte view (torch.bool [B, AP]) for envs [env_lo, env_lo + count): 16 mask entries per 128-bit store.
+__global__ void __launch_bounds__(256) mask_bytes_kernel(ge_batch d, int env_lo, long long total16) {
+    const int per_env = d.AP >> 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += (long long)gridDim.x * blockDim.x) {
+        const int b = env_lo + (int)(i / per_env), c = (int)(i % per_env);
+        const uint32_t word = c < 2 * d.AW ? d.mask_bits[(size_t)b * d.AW + (c >> 1)] : 0u;
+        const uint32_t bits = (word >> ((c & 1) * 16)) & 0xffffu;
+        reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP)[c] =
+            make_uint4(expand4(bits), expand4(bits >> 4), expand4(bits >> 8), expand4(bits >> 12));
+    }
+}
+
 __global__ void stats_kernel(ge_batch d, double *out4) {
     __shared__ double sh[4][32];
     double a[4] = {0, 0, 0, 0};
@@ -439,6 +451,9 @@ int ge_group_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 bool ge_incr_eligible(const ge_batch *d);
 int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_incr_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
+
+// eval heuristic kernels (ge_heuristics.cu)
+int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
 static int check_batch(const ge_batch *d) {
@@ -526,6 +541,7 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
     size_t smem;
     cudaStream_t st = (cudaStream_t)stream;
     if ((what & 3) && !d->w64) return fail(GE_ERR_ARG, "ge_prepare needs w64");
+    if ((what & 8) && !d->w64 && d->kind != GE_MAX_INDEPENDENT_SET) return fail(GE_ERR_ARG, "ge_prepare needs w64");
     if (what & 1) {
         bool sssp = d->kind == GE_SHORTEST_PATH || d->kind == GE_LONGEST_PATH || (d->kind == GE_STEINER_TREE && d->n_dests == 1);
         bool mst = d->kind == GE_STEINER_TREE && d->n_dests == d->N - 1;
@@ -537,10 +553,16 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
             if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
             if ((rc = set_smem(prep_mst_kernel, smem))) return rc;
             prep_mst_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, wpw);
-        } else if (d->kind == GE_STEINER_TREE || d->kind == GE_TSP || d->kind == GE_MULTICAST_ROUTING) {
-            return fail(GE_ERR_UNSUPPORTED, "tie-dependent eval heuristic (Kou / Christofides / union-of-paths) is not provided; see DESIGN.md");
+        } else if (d->kind == GE_MULTICAST_ROUTING) {
+            if ((rc = ge_heuristics_launch(d, 1, st))) return rc;
+        } else if (d->kind == GE_STEINER_TREE || d->kind == GE_TSP) {
+            return fail(GE_ERR_UNSUPPORTED, "the reference's Kou / Christofides value is defined by networkx iteration order and is not "
+                                            "provided; ask for the labelled alternative (what bit 3 -> heuristic_alt)");
         }
         GE_CUDA_OK(cudaGetLastError());
+    }
+    if ((what & 8) && (d->kind == GE_STEINER_TREE || d->kind == GE_TSP || d->kind == GE_MAX_INDEPENDENT_SET)) {
+        if ((rc = ge_heuristics_launch(d, 8, st))) return rc;
     }
     if ((what & 2) && d->kind == GE_MULTICAST_ROUTING) {
         if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -653,6 +675,21 @@ int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *strea
 
 int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }
 
+int ge_mask_bytes_current(const ge_batch *d) { return d && d->mask_bytes && !ge_incr_eligible(d); }
+
+int ge_mask_bytes(const ge_batch *d, int env_lo, int count, void *stream) {
+    int rc = check_batch(d);
+    if (rc) return rc;
+    if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+    if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
+    const long long total16 = (long long)count * (d->AP >> 4);
+    long long blocks = (total16 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    mask_bytes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, total16);
+    GE_CUDA_OK(cudaGetLastError());
+    return GE_OK;
+}
+
 const char *ge_step_kernel_name(const ge_batch *d, int sampled) {
     static thread_local char name[96];
     if (!d) return "";
@@ -694,6 +731,7 @@ static int step_host_enqueue(const ge_batch *d, const int32_t *h_actions, int32_
     }
     if (h_mask) {
         if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+        if (!ge_mask_bytes_current(d) && (rc = ge_mask_bytes(d, 0, d->B, (void *)st))) return rc;
         GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
     }
     return GE_OK;
@@ -780,7 +818,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     if (d->adj_bits) o->adj_bits = d->adj_bits + (adj_tiled(*d) ? (b >> 5) * (size_t)d->N * 32 * d->NW : b * (size_t)d->ADJS);
     ADV(rev, d->MP); ADV(esrc, d->MP); ADV(wsort, d->MP); ADV(wcode, d->MP); ADV(wmin, 1); ADV(wmat, (size_t)d->N * d->N);
     ADV(src, 1); ADV(dest, 1); ADV(target_bits, d->NW); ADV(node_cost, d->N); ADV(node_xy, 2 * d->N); ADV(max_dist32, 1);
-    ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(heuristic, 1); ADV(features, 5 * d->N);
+    ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(heuristic, 1); ADV(heuristic_alt, 1); ADV(features, 5 * d->N);
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
     ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
     ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);
@@ -810,6 +848,7 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
             GE_CUDA_OK(cudaMemcpyAsync(h_mask_bits, d->mask_bits, sizeof(uint32_t) * B * d->AW, cudaMemcpyDeviceToHost, st));
         if (h_mask) {
             if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
+            if (!ge_mask_bytes_current(d) && (rc0 = ge_mask_bytes(d, 0, d->B, stream))) return rc0;
             GE_CUDA_OK(cudaMemcpyAsync(h_mask, d->mask_bytes, B * d->AP, cudaMemcpyDeviceToHost, st));
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));

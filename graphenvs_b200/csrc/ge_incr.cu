@@ -35,25 +35,22 @@ constexpr u64 KEY_NONE = ~0ull;
                         // 0.70 / 0.84 / 0.96 G env-steps/s at cfg3 for 4 / 6 / 8 blocks per SM.
 #endif
 
+// The incremental kernels keep only the PACKED mask current.  Writing the byte view as well meant one scattered 1-byte
+// store per changed edge, each a 32-byte sector read-modify-write in HBM: 2.3 KB of the 4.7 KB a Multicast step moved
+// (profiles/r01_final_step_kernel_cfg5_multicast.md, 2.55x the useful bytes).  The byte view (torch.bool for a policy)
+// is expanded on demand by ge_mask_bytes (ge_api.cu) in one coalesced pass.
 __device__ __forceinline__ void mask_set(const ge_batch &d, int b, int e) {
     atomicOr(&d.mask_bits[(size_t)b * d.AW + (e >> 5)], 1u << (e & 31));
-    if (d.mask_bytes) d.mask_bytes[(size_t)b * d.AP + e] = 1;
 }
 __device__ __forceinline__ void mask_clear(const ge_batch &d, int b, int e) {
     atomicAnd(&d.mask_bits[(size_t)b * d.AW + (e >> 5)], ~(1u << (e & 31)));
-    if (d.mask_bytes) d.mask_bytes[(size_t)b * d.AP + e] = 0;
 }
 
-// Group-wide zero fill of an env's mask (packed + bytes) with 128-bit stores.
+// Group-wide zero fill of an env's packed mask.
 template <int G>
 __device__ __forceinline__ void mask_zero(const ge_batch &d, int b, int lane) {
     uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
     for (int w = lane; w < d.AW; w += G) mb[w] = 0;
-    if (d.mask_bytes) {
-        uint4 *p = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = lane; i < (d.AP >> 4); i += G) p[i] = z;
-    }
 }
 
 // State init + first mask (tail of reset()) for the tree-growing kinds.  Returns nothing; all lanes.
@@ -172,8 +169,15 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     bool violated = false;
     float rew = -w;
     if (mc) {                                                               // multicast_routing.py:191-266
-        const int u = d.esrc[(size_t)b * d.MP + a];
-        dv = __fadd_rn(d.dist32[(size_t)b * N + u], w);                     // float32 add (:228)
+        if (d.parenting >= 3) {
+            // `a` is valid => it IS the running-argmin edge of v, whose key holds float32(dist[src a] + delay[a]) in its
+            // high word: the very value of :228, computed with the same float32 add when the edge was folded in.
+            // No esrc[a] / dist[u] round trip (two scattered sectors).
+            dv = __uint_as_float((uint32_t)(reinterpret_cast<const u64 *>(d.bestkey)[(size_t)b * N + v] >> 32));
+        } else {
+            const int u = d.esrc[(size_t)b * d.MP + a];
+            dv = __fadd_rn(d.dist32[(size_t)b * N + u], w);                 // float32 add (:228)
+        }
         r.sol = -1.0;
         if (v_is_target) {
             float lim = __fadd_rn(d.max_dist32[b], 1e-4f);                  // float32 compare under numpy 2 (:232)
@@ -300,14 +304,6 @@ __global__ void __launch_bounds__(256) incr_mis_step_kernel(ge_batch d, int32_t 
     publish(d, out, b, a, r, nsteps);
     if (r.done && (d.flags & GE_FLAG_AUTO_RESET)) {
         for (int wi = 0; wi < d.NW; ++wi) { d.node_bits[(size_t)b * d.NW + wi] = 0; mb[wi] = tail_mask(N, wi); }
-        if (d.mask_bytes) {
-            uint4 *p = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
-            for (int i = 0; i < (d.AP >> 4); ++i) {
-                int rem = N - 16 * i;
-                uint32_t bits = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-                p[i] = make_uint4(expand4(bits), expand4(bits >> 4), expand4(bits >> 8), expand4(bits >> 12));
-            }
-        }
         d.cost[b] = 0.0;
         d.head[b] = 0;
         *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = make_int4(0, 0, 0, 0);
@@ -315,7 +311,6 @@ __global__ void __launch_bounds__(256) incr_mis_step_kernel(ge_batch d, int32_t 
     }
     d.node_bits[(size_t)b * d.NW + (a >> 5)] |= 1u << (a & 31);
     mb[a >> 5] &= ~(1u << (a & 31));
-    if (d.mask_bytes) d.mask_bytes[(size_t)b * d.AP + a] = 0;
     d.cost[b] = (double)cost32;
     *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = c;
     if (r.done) d.done[b] = 1;
@@ -327,14 +322,6 @@ __global__ void __launch_bounds__(256) incr_mis_reset_kernel(ge_batch d, const u
     if (select && !select[b]) return;
     const int N = d.N;
     for (int wi = 0; wi < d.NW; ++wi) { d.node_bits[(size_t)b * d.NW + wi] = 0; d.mask_bits[(size_t)b * d.AW + wi] = tail_mask(N, wi); }
-    if (d.mask_bytes) {
-        uint4 *p = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
-        for (int i = 0; i < (d.AP >> 4); ++i) {
-            int rem = N - 16 * i;
-            uint32_t bits = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-            p[i] = make_uint4(expand4(bits), expand4(bits >> 4), expand4(bits >> 8), expand4(bits >> 12));
-        }
-    }
     d.cost[b] = 0.0;
     d.head[b] = 0;
     d.done[b] = 0;
@@ -348,7 +335,7 @@ bool ge_incr_eligible(const ge_batch *d) {
     if (d->flags & GE_FLAG_FORCE_WARP) return false;
     if (d->kind == GE_STEINER_TREE) return d->rev != nullptr;
     if (d->kind == GE_MULTICAST_ROUTING)
-        return d->parenting >= 2 && d->esrc != nullptr && (d->parenting >= 3 ? d->bestkey != nullptr : d->rev != nullptr);
+        return d->parenting >= 3 ? d->bestkey != nullptr : (d->parenting == 2 && d->esrc != nullptr && d->rev != nullptr);
     if (d->kind == GE_MAX_INDEPENDENT_SET) return d->N > 64;  // N <= 64 is the lane-per-env family's
     return false;
 }

@@ -15,8 +15,6 @@ from typing import Optional
 
 import numpy as np
 
-from . import nx_heuristics
-
 
 @dataclass
 class Instance:
@@ -31,6 +29,7 @@ class Instance:
     max_distance: Optional[float] = None  # Multicast: value of the MAX_DISTANCE column (None -> from u01 on device)
     u01: Optional[float] = None           # Multicast: the reference's np.random.rand() draw
     heuristic: Optional[float] = None     # None -> computed on the device when is_eval_env
+    edge_order: Optional[list] = None     # undirected edges in the order gnm_random_graph inserted them
     features: Optional[np.ndarray] = None  # float32 [N, 5]; None -> computed on the device
 
 
@@ -93,46 +92,6 @@ def _undirected_edges(adj):
         seen.add(u)
 
 
-def multicast_union_of_paths(adj, weight, src, dests):
-    """MulticastRouting eval heuristic (multicast_routing.py:107-115): total weight of the union of the
-    FIRST-FOUND shortest paths src -> each destination.  The value depends on networkx's tie order, so the
-    search restates nx `_dijkstra_multisource` literally (nx:algorithms/shortest_paths/weighted.py:853-881):
-    heap of (dist, insertion counter, node), neighbours in adjacency insertion order, a predecessor is
-    replaced only by a strictly shorter path; paths are rebuilt from the first predecessor; the edge set and
-    its sum use the same Python set / list operations as the reference."""
-    from heapq import heappop, heappush
-    from itertools import count, islice
-    dist, seen, pred = {}, {src: 0}, {}
-    c = count()
-    fringe = [(0, next(c), src)]
-    while fringe:
-        d_v, _, v = heappop(fringe)
-        if v in dist:
-            continue
-        dist[v] = d_v
-        for u in adj[v]:
-            vu = d_v + weight(v, u)
-            if u in dist:
-                continue
-            if u not in seen or vu < seen[u]:
-                seen[u] = vu
-                heappush(fringe, (vu, next(c), u))
-                pred[u] = v
-    paths = {src: [src]}
-    for v in islice(dist, 1, None):
-        paths[v] = paths[pred[v]] + [v]
-    edges = set()
-    for d in dests:
-        path = paths[d]
-        for u, v in zip(path[:-1], path[1:]):
-            edges.add((u, v))
-    return sum([weight(u, v) for u, v in edges])
-
-
-def _weight_map(links, w64):
-    return {(int(u), int(v)): float(w) for (u, v), w in zip(links.tolist(), w64)}
-
-
 def generate_instance(env_id, p):
     """Instance of `env_id` with constructor parameters `p` (spec.check_ctor_args), consuming the
     global `random` / `numpy.random` streams exactly like the reference's reset()."""
@@ -154,7 +113,7 @@ def generate_instance(env_id, p):
         adj.append(dict())
     links = np.array([(u, v) for u in range(N) for v in adj[u]], dtype=np.int32).reshape(-1, 2)
     M = links.shape[0]
-    ins = Instance(n_nodes=N, links=links, w64=np.ones(M, dtype=np.float64))
+    ins = Instance(n_nodes=N, links=links, w64=np.ones(M, dtype=np.float64), edge_order=edge_order)
     rnd = np.random
 
     def matrix_delay(unweighted_lo, unweighted_hi, div):
@@ -174,8 +133,6 @@ def generate_instance(env_id, p):
         ins.w64 = matrix_delay(1, 2, 1.0)                           # steiner_tree.py:62-68
         d = rnd.choice(N, p["n_dests"] + 1, replace=False)          # :73
         ins.src, ins.dests = int(d[0]), d[1:].astype(np.int32)      # :89
-        if p.get("is_eval_env") and 1 < p["n_dests"] < N - 1:       # :84-85 Kou: defined by networkx's iteration order
-            ins.heuristic = nx_heuristics.steiner_kou(N, edge_order, _weight_map(links, ins.w64), d)
     elif env_id == "TSP-v0":
         wmap = {}
         if p.get("spatial"):                                        # tsp.py:79-86
@@ -190,12 +147,8 @@ def generate_instance(env_id, p):
             for u, v in _undirected_edges(adj):
                 wmap[(u, v)] = (rnd.randint(3, 10) / 10.0) if weighted else (rnd.randint(1, 2) / 1.0)
         ins.w64 = np.array([wmap[(u, v)] if (u, v) in wmap else wmap[(v, u)] for u, v in links], dtype=np.float64)
-        if p.get("is_eval_env"):                                    # tsp.py:114-117 Christofides (networkx order)
-            ins.heuristic = nx_heuristics.tsp_christofides(N, edge_order, _weight_map(links, ins.w64))
     elif env_id == "MaxIndependentSet-v0":                          # max_independent_set.py:53-57
         ins.node_cost = (rnd.randint(3, 10, size=N) / 10.0) if weighted else (rnd.randint(1, 2, size=N) / 1.0)
-        if p.get("is_eval_env") and not weighted:                   # max_independent_set.py:62-65 Ramsey (networkx order)
-            ins.heuristic = nx_heuristics.mis_ramsey(N, edge_order)
     elif env_id == "DensestSubgraph-v0":
         pass
     elif env_id == "MulticastRouting-v0":
@@ -203,11 +156,6 @@ def generate_instance(env_id, p):
         ins.src = 0
         ins.dests = rnd.choice(np.arange(1, N), size=p["n_dests"], replace=False).astype(np.int32)  # :95
         ins.u01 = float(rnd.rand())                                 # :103 (max_distance itself needs the SSSP)
-        if p.get("is_eval_env"):                                    # :107-115, tie-order dependent => host restatement
-            wm = {}
-            for (u, v), w in zip(links.tolist(), ins.w64):
-                wm[(u, v)] = w
-            ins.heuristic = float(multicast_union_of_paths(adj, lambda u, v: wm[(u, v)], 0, [int(t) for t in ins.dests]))
     elif env_id == "DistributionCenter-v0":
         ins.w64 = matrix_delay(1, 2, 1.0)                           # distribution_center.py:74-80
         ins.node_cost = rnd.randint(1, 4, size=N) / 1.0             # :82

@@ -91,11 +91,12 @@ class GraphEnv(_Base):
             return -1                                              # densest_subgraph.py:88
         if kind == "MaxIndependentSet-v0" and self.params["weighted"]:
             return -1                                              # max_independent_set.py:66-67
-        if self._heur_on_device or kind == "MulticastRouting-v0" or self.instance.heuristic is not None:
-            return float(self.core.t["heuristic"][0].item())   # device value, or the host value loaded with the instance
+        if self._heur_on_device or self.instance.heuristic is not None:
+            return float(self.core.t["heuristic"][0].item())   # device value, or a host value loaded with the instance
         if not self._warned:
-            warnings.warn("%s: the reference's eval heuristic here is defined by networkx's iteration order (Kou / Christofides / "
-                          "Ramsey) and networkx is not importable; heuristic_solution = nan" % kind)
+            warnings.warn("%s: the reference's eval heuristic here (Kou / Christofides / Ramsey) is defined by networkx's set "
+                          "iteration order and is not reproduced: heuristic_solution = nan; info['heuristic_device'] carries "
+                          "the device-computed %s" % (kind, self.core.heuristic_device_name))
             self._warned = True
         return float("nan")
 
@@ -143,6 +144,9 @@ class GraphEnv(_Base):
             info["solution_cost"] = sol
         if done_b or self.env_id in _EVERY_STEP_HEURISTIC:
             info["heuristic_solution"] = self._heuristic()
+            if self.is_eval_env and c.heuristic_device_name and not (self.env_id == "MaxIndependentSet-v0" and self.params["weighted"]):
+                info["heuristic_device"] = float(c.t["heuristic_alt"][0].item())
+                info["heuristic_device_name"] = c.heuristic_device_name
         if self.env_id == "LongestPath-v0":                        # longest_path.py:160,166
             self._track.append((self._head, a))
             info["edges_taken"] = self._track

@@ -18,12 +18,26 @@ class EnvSpec:
     defaults: tuple      # ((kwarg, default), ...) after n_nodes, n_edges
 
     def heuristic_on_device(self, p):
-        """Eval heuristics whose VALUE is tie-independent run on the GPU."""
-        if self.kind in (0, 1):
+        """Eval heuristics the GPU computes with the REFERENCE'S value: the tie-independent ones (Dijkstra
+        for ShortestPath / LongestPath / SteinerTree n_dests=1, MST weight for n_dests=N-1) and Multicast's union of
+        first-found shortest paths (networkx's pop order restated in csrc/ge_heuristics.cu)."""
+        if self.kind in (0, 1, 6):
             return True
         if self.kind == 2:
             return p["n_dests"] == 1 or p["n_dests"] == p["n_nodes"] - 1
         return False
+
+    def heuristic_alternative(self, p):
+        """Name of the labelled alternative heuristic the GPU computes where the reference's value is defined by networkx's
+        set / dict iteration order (Kou, Christofides, Ramsey), else None.  Reported under
+        info['heuristic_device'], never as info['heuristic_solution']."""
+        if self.kind == 2 and not self.heuristic_on_device(p):
+            return "steiner_shortest_path_heuristic"      # Takahashi-Matsuyama, 2-approximation like Kou
+        if self.kind == 3:
+            return "tsp_nearest_neighbour_walk"
+        if self.kind == 4:
+            return "mis_greedy_min_degree"
+        return None
 
 
 ENV_SPECS = {

@@ -23,7 +23,7 @@
  *   ge_obs_graph      utils.devectorize_graph (utils.py:14-23) applied on the device: (x, edge_features, edge_index)
  *   ge_features       feature_extraction.generate_features (feature_extraction.py:6-37)
  *   ge_prepare        reset-time derived data: eval heuristics (shortest_path.py:88-90,
- *                     longest_path.py:103-106, steiner_tree.py:77-85), Multicast max_distance
+ *                     longest_path.py:103-106, steiner_tree.py:77-85, multicast_routing.py:107-115), Multicast max_distance
  *                     (multicast_routing.py:98-103), DistributionCenter in-range tables
  *                     (distribution_center.py:25-26,113-116)
  *   ge_generate       instance generation of reset() (shortest_path.py:54-75 and peers) --
@@ -130,6 +130,9 @@ typedef struct ge_batch {
     int32_t *targets;             /* [B, n_targets] DistributionCenter target node ids */
     uint32_t *in_range;           /* [B, n_targets, NW] nodes within max_distance of each target */
     double *heuristic;            /* [B]      info['heuristic_solution'] */
+    double *heuristic_alt;        /* [B]      info['heuristic_device']: labelled alternative where the reference's value is defined by
+                                              networkx iteration order (Steiner shortest-path heuristic, TSP nearest neighbour, greedy
+                                              MIS; csrc/ge_heuristics.cu), or NULL */
     float *features;              /* [B, N, 5] structural features or NULL (zeros in obs) */
 
     /* ---- dynamic state ---- */
@@ -145,7 +148,10 @@ typedef struct ge_batch {
                                               tree / nodes taken, popcount of the mask, constraints satisfied */
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
-    uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL */
+    uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL.  Kept current by the kernels that
+                                              rewrite the whole mask; the INCREMENTAL-mask kernels (SteinerTree, Multicast p >= 2,
+                                              MaxIndependentSet N > 64: ge_mask_bytes_current() == 0) update only the packed mask and
+                                              the byte view is produced on demand by ge_mask_bytes */
     uint32_t *mask_mirror;        /* [B, AW]  optional second destination of every packed-mask write, e.g. PINNED HOST memory
                                               (zero-copy results, see ge_step_host); honoured by the kernels that rewrite
                                               the whole mask, not by the incremental ones (ge_mask_mirror_supported) */
@@ -180,7 +186,9 @@ int ge_step_smem_bytes(const ge_batch *batch);
 
 /* Fills every DERIVED graph array whose pointer is set: adj_bits, wmat, wsort, rev, esrc, wmin. */
 int ge_build_adjacency(const ge_batch *batch, void *stream);
-/* what: bit0 heuristics (SSSP / MST where the reference's value is tie-independent),
+/* what: bit0 heuristics with the reference's value: SSSP / MST (tie-independent) and Multicast's union of first-found
+ *            shortest paths (networkx's pop order restated on the device),
+ *       bit3 labelled alternative heuristics -> heuristic_alt (SteinerTree 1 < n_dests < N-1, TSP, MaxIndependentSet),
  *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw); u01 == NULL takes the draw
  *            ge_generate left in max_dist32 (a pure function of seed and global env id),
  *       bit2 DistributionCenter in-range tables. */
@@ -223,6 +231,12 @@ const char *ge_step_kernel_name(const ge_batch *batch, int sampled);
  * to it directly over PCIe -- no copy calls, one launch, one stream sync.  The packed mask arrives the same
  * way when batch->mask_mirror == h_mask_bits and ge_mask_mirror_supported(batch), otherwise by one copy. */
 int ge_mask_mirror_supported(const ge_batch *batch);
+/* 1 when every ge_step / ge_reset leaves mask_bytes equal to the packed mask; 0 when the byte view must be refreshed with
+ * ge_mask_bytes before it is read (incremental-mask kernels: a scattered byte store per changed edge was 2.3 KB of HBM
+ * traffic per Multicast step against 1.8 KB of useful bytes). */
+int ge_mask_bytes_current(const ge_batch *batch);
+/* Expands the packed mask of envs [env_lo, env_lo + count) into mask_bytes (one coalesced pass). */
+int ge_mask_bytes(const ge_batch *batch, int env_lo, int count, void *stream);
 int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                  float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask,
                  uint32_t *h_mask_bits, void *stream);
