@@ -270,6 +270,7 @@ class BatchedGraphEnv:
         for k in ("wcode", "dfa"):
             T.pop(k, None)
         self._sync_desc()
+        self.desc.dfa_bytes = 0
         w = T.get("w64")
         if w is None or M == 0:
             return False
@@ -308,6 +309,7 @@ class BatchedGraphEnv:
         T["wcode"] = code
         T["dfa"] = torch.from_numpy(np.concatenate([np.array([S, W], dtype=np.uint8), tab.ravel(), expand])).to(self.device)
         self._sync_desc()
+        self.desc.dfa_bytes = int(T["dfa"].numel())
         return True
 
     def export_instances(self, env_lo=0, count=None):

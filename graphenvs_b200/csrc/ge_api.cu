@@ -452,6 +452,10 @@ bool ge_incr_eligible(const ge_batch *d);
 int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_incr_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 
+// dedicated DistributionCenter kernels (ge_dc.cu)
+bool ge_dc_eligible(const ge_batch *d);
+int ge_dc_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
+int ge_dc_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 // eval heuristic kernels (ge_heuristics.cu)
 int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
@@ -507,7 +511,6 @@ int ge_fill_layout(ge_batch *d) {
     d->NW = (d->N + 31) / 32;
     d->MW = (d->M + 31) / 32;
     d->acc_stride = d->B;
-    d->reserved0 = 0;
     d->A = is_edge_kind(d->kind) ? d->M : d->N;
     d->AW = (d->A + 31) / 32;
     d->AP = (d->A + 15) & ~15;
@@ -590,6 +593,7 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     if (ge_lane_eligible(d)) return ge_lane_reset(d, select, (cudaStream_t)stream);
     if (ge_group_eligible(d)) return ge_group_reset(d, select, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_reset(d, select, (cudaStream_t)stream);
+    if (ge_dc_eligible(d)) return ge_dc_reset(d, select, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -607,6 +611,7 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_group_eligible(d)) return ge_group_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
+    if (ge_dc_eligible(d)) return ge_dc_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     int blocks, wpw;
     size_t smem;
     if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
@@ -700,6 +705,7 @@ const char *ge_step_kernel_name(const ge_batch *d, int sampled) {
     else if (ge_incr_eligible(d)) {
         if (d->kind == GE_MAX_INDEPENDENT_SET) { fam = "incr_mis_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }
         else { fam = "incr_tree_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,G=%d", sampled, d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32); }
+    } else if (ge_dc_eligible(d)) { fam = "dc_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled);
     } else { fam = "step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,MINB=%d", sampled, (d->kind == GE_DISTRIBUTION_CENTER && d->wcode && d->dfa) ? 6 : 4); }
     snprintf(name, sizeof(name), "%s<%s>", fam, shape);
     return name;

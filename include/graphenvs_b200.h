@@ -93,7 +93,7 @@ typedef struct ge_batch {
     int32_t RP, MP, ADJS;         /* strides: row_ptr (ints), col/w (elements), adj_bits (words) per env */
     int32_t acc_stride;           /* elements between the 4 components of `acc` (= B of the batch the array was allocated for;
                                      ge_fill_layout sets it to B, ge_batch_slice keeps the parent's) */
-    int32_t reserved0;
+    int32_t dfa_bytes;            /* size of the `dfa` array in bytes (0 = unknown) */
     double max_distance;          /* DistributionCenter cutoff */
 
     /* ---- graph store (static per instance) ---- */

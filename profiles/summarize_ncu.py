@@ -68,6 +68,9 @@ def main():
             f.write('\nHottest source lines (launch 1; share of warp instructions / of stall samples):\n\n| file:line | instr % | samples % | source |\n|---|---|---|---|\n')
             for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
                 f.write('| %s:%d | %.1f | %.1f | `%s` |\n' % (k[0], k[1], 100 * v[0] / max(ti, 1), 100 * v[1] / max(ts, 1), v[2].replace('|', '\\|')))
+            f.write('\nLines with the most stall samples (launch 1):\n\n| file:line | samples % | instr % | source |\n|---|---|---|---|\n')
+            for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+                f.write('| %s:%d | %.1f | %.1f | `%s` |\n' % (k[0], k[1], 100 * v[1] / max(ts, 1), 100 * v[0] / max(ti, 1), v[2].replace('|', '\\|')))
         except Exception as e:  # pragma: no cover
             f.write('\n(source page unavailable: %s)\n' % e)
     print(open(out).read())
