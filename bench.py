@@ -527,6 +527,56 @@ def feature_costs(D):
     return out
 
 
+def turnover_costs(D, K=300):
+    """Reset-INCLUSIVE throughput (every reference reset() builds a new graph, e.g.
+    shortest_path.py:47-98): step + instance turnover from a resident pool (graphenvs_b200/pool.py: done envs copy their next
+    instance from a bank of prepared instances and are reset; a background stream keeps regenerating banks) next to the
+    state-only number under the SAME launch protocol (plain launches from Python, no L2 flush, one event pair around K steps)."""
+    import torch
+    from graphenvs_b200 import BatchedGraphEnv
+    from graphenvs_b200.pool import InstancePool
+    out = {}
+    for wl in ("cfg1_shortest_path", "cfg5_distcenter"):
+        env_id, N, E, kw, B, _, desc = WORKLOADS[wl]
+        res = {"workload": desc}
+        for mode in ("state_only_auto_reset_same_graph", "pool_turnover"):
+            env = BatchedGraphEnv(env_id, B, N, E, device=D.dev, auto_reset=(mode != "pool_turnover"), **kw)
+            env.generate(seed=SEED)
+            env.reset()
+            env.enable_env_clock()
+            pool = InstancePool(env, banks=3, seed=11, background=True) if mode == "pool_turnover" else None
+
+            def one():
+                env.step_sampled(SEED, 0)
+                if pool is not None:
+                    pool.turn_over()
+            for _ in range(20):
+                one()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ep0 = float(env.stats()[0].item())
+            a.record()
+            for _ in range(K):
+                one()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / K
+            eps = float(env.stats()[0].item()) - ep0
+            r = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "episodes_finished": eps,
+                 "mean_episode_steps": (B * K / eps) if eps else None, "launches_per_step": 1 if pool is None else 3}
+            if pool is not None:
+                pool.close()
+                r["pool"] = {"banks": pool.G, "instances_resident": pool.G * B, "banks_regenerated_in_background": pool.regenerated,
+                             "fresh_instances_generated": pool.regenerated * B, "instances_consumed": eps,
+                             "note": "an instance is reused when episodes end faster than the background stream regenerates banks "
+                                     "(fresh_instances_generated / instances_consumed = fraction of episodes on a never-seen graph)"}
+            res[mode] = r
+            del env, pool
+            torch.cuda.empty_cache()
+        out[wl] = res
+    return out
+
+
 def run_ours(args):
     import torch
     D = Dist()
@@ -575,6 +625,7 @@ def run_ours(args):
                             "what": "one step of all 1,048,576 envs = the Multicast launch + the DistributionCenter launch, back to back"}
 
     feats = feature_costs(D) if (world == 1 and not args.only_headline and not args.envs) else None
+    turn = turnover_costs(D) if (world == 1 and not args.only_headline and not args.envs and not args.no_turnover) else None
 
     if rank == 0:
         line = {
@@ -598,6 +649,7 @@ def run_ours(args):
             "workloads": workloads,
             "cfg5_strong_scaling": cfg5,
             "feature_extraction_us_per_env": feats,
+            "instance_turnover": turn,
             "bench_wall_s": time.time() - t_all,
         }
         if "cpu_baseline" in head:
@@ -625,6 +677,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the all-workloads pass, config 5 and the feature costs")
     ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--no-turnover", action="store_true")
     ap.add_argument("--no-e2e-obs", dest="e2e_obs", action="store_false")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
     ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],

@@ -95,7 +95,7 @@ class StepOut(C.Structure):
 
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
-           "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
+           "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_pool_refill", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
            "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined",
            "ge_step_host_release", "ge_mask_mirror_supported", "ge_mask_bytes_current", "ge_mask_bytes", "ge_stats"]
 
@@ -125,6 +125,7 @@ def lib():
     L.ge_features.argtypes = [BP, _P]
     L.ge_generate.argtypes = [BP, C.c_uint64, _P, _P, _P, _P, _P]
     L.ge_generate_fallbacks.argtypes = [_P]
+    L.ge_pool_refill.argtypes = [BP, BP, C.c_int, _P, C.c_int, _P, _P, _P]
     L.ge_reset.argtypes = [BP, _P, _P]
     L.ge_step.argtypes = [BP, _P, C.POINTER(StepOut), _P]
     L.ge_sample_actions.argtypes = [BP, C.c_uint64, C.c_uint32, _P, _P]

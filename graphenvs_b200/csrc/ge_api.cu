@@ -761,8 +761,8 @@ struct HostStepGraph {
 HostStepGraph g_hsg[HSG_SLOTS];
 int g_hsg_next = 0;
 std::mutex g_hsg_mu;
-cudaStream_t g_side[HSG_MAX_CHUNKS];
-cudaEvent_t g_fork, g_join[HSG_MAX_CHUNKS];
+cudaStream_t g_side[2];                                  // copy-in lane, write-back lane (the kernels stay on the caller's stream)
+cudaEvent_t g_fork, g_in[HSG_MAX_CHUNKS], g_stepped[HSG_MAX_CHUNKS], g_join;
 bool g_side_ready = false;
 
 cudaGraphExec_t hsg_find(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks) {
@@ -902,22 +902,26 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
     return GE_OK;
 }
 
-// One slice of the pipelined step on stream `s`: actions in, step, results out (enqueue only).
-static int pipelined_enqueue_slice(const ge_batch *d, int lo, int n, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
-                                   float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits, cudaStream_t s) {
+// The three stages of one slice of the pipelined step (enqueue only).
+static int pipelined_copy_in(const ge_batch *d, int lo, int n, const int32_t *h_actions, int32_t *d_actions, cudaStream_t s) {
+    GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    return GE_OK;
+}
+static int pipelined_step(const ge_batch *d, int lo, int n, int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
     ge_batch sl;
     int rc = ge_batch_slice(d, lo, n, &sl);
     if (rc) return rc;
     ge_step_out so = {out->reward + lo, out->flags + lo, out->solution_cost + lo};
-    GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
-    rc = ge_step(&sl, d_actions + lo, &so, (void *)s);
-    if (rc) return rc;
+    return ge_step(&sl, d_actions + lo, &so, (void *)s);
+}
+static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_out *out, float *h_reward, ge_step_flags *h_flags,
+                                double *h_solution_cost, uint32_t *h_mask_bits, cudaStream_t s) {
     const size_t bytes = (size_t)n * (16 + 4 * (size_t)d->AW);
     int blocks = (int)((bytes / 16 + 255) / 256);
     if (blocks > 32) blocks = 32;     // a handful of CTAs saturate PCIe; the rest of the GPU keeps stepping the next slice
     if (blocks < 1) blocks = 1;
-    writeback_kernel<<<blocks, 256, 0, s>>>(so.reward, so.flags, so.solution_cost, sl.mask_bits, h_reward + lo, h_flags + lo,
-                                            h_solution_cost ? h_solution_cost + lo : nullptr,
+    writeback_kernel<<<blocks, 256, 0, s>>>(out->reward + lo, out->flags + lo, out->solution_cost + lo, d->mask_bits + (size_t)lo * d->AW,
+                                            h_reward + lo, h_flags + lo, h_solution_cost ? h_solution_cost + lo : nullptr,
                                             h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
@@ -942,32 +946,44 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
     }
     if (!exec) {
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
-        // forked sequence for the following calls
+        // three-lane sequence for the following calls
         for (int i = 0; i < chunks; ++i) {
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
-            if ((rc = pipelined_enqueue_slice(d, lo, n, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
+            if ((rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
+            if ((rc = pipelined_step(d, lo, n, d_actions, out, st))) return rc;
+            if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lock(g_hsg_mu);
         if (!g_side_ready) {
+            for (int i = 0; i < 2; ++i) GE_CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
             for (int i = 0; i < HSG_MAX_CHUNKS; ++i) {
-                GE_CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
-                GE_CUDA_OK(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+                GE_CUDA_OK(cudaEventCreateWithFlags(&g_in[i], cudaEventDisableTiming));
+                GE_CUDA_OK(cudaEventCreateWithFlags(&g_stepped[i], cudaEventDisableTiming));
             }
             GE_CUDA_OK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+            GE_CUDA_OK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
             g_side_ready = true;
         }
+        // Three lanes: copy-in chain (g_side[0]) -> step-kernel chain (caller's stream) -> write-back chain (g_side[1]).
+        // The kernels of the slices run ONE AFTER THE OTHER: launched side by side they would share the GPU, finish
+        // together, and every write-back would start as late as after a single big kernel (measured: no gain).  Chained,
+        // slice i's results cross PCIe while slice i+1 steps.
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc2 = GE_OK;
-            bool ok = cudaEventRecord(g_fork, st) == cudaSuccess;
+            cudaStream_t s_in = g_side[0], s_out = g_side[1];
+            bool ok = cudaEventRecord(g_fork, st) == cudaSuccess && cudaStreamWaitEvent(s_in, g_fork, 0) == cudaSuccess &&
+                      cudaStreamWaitEvent(s_out, g_fork, 0) == cudaSuccess;
             for (int i = 0; ok && i < chunks && rc2 == GE_OK; ++i) {
                 const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
-                cudaStream_t s = i == 0 ? st : g_side[i];        // slice 0 stays on the origin stream
-                if (i) ok = ok && cudaStreamWaitEvent(s, g_fork, 0) == cudaSuccess;
-                rc2 = pipelined_enqueue_slice(d, lo, n, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s);
-                if (i) ok = ok && cudaEventRecord(g_join[i], s) == cudaSuccess && cudaStreamWaitEvent(st, g_join[i], 0) == cudaSuccess;
+                rc2 = pipelined_copy_in(d, lo, n, h_actions, d_actions, s_in);
+                ok = ok && cudaEventRecord(g_in[i], s_in) == cudaSuccess && cudaStreamWaitEvent(st, g_in[i], 0) == cudaSuccess;
+                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, d_actions, out, st);
+                ok = ok && cudaEventRecord(g_stepped[i], st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_stepped[i], 0) == cudaSuccess;
+                if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s_out);
             }
+            ok = ok && cudaEventRecord(g_join, s_out) == cudaSuccess && cudaStreamWaitEvent(st, g_join, 0) == cudaSuccess;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (ok && rc2 == GE_OK && e == cudaSuccess && graph) {
                 cudaGraphExec_t ex = nullptr;

@@ -23,6 +23,8 @@
 // 190 us/env at TSP N=200 dense, 73 us/env at N=500) is kept as features_warp_kernel for N > 1024.
 // Sums are reassociated relative to networkx (sigma sums are integers < 2^53 => exact; delta and
 // pagerank differ by fp64 rounding, ~1e-16 relative; the tests compare at 1e-5 in float32).
+#include <cstdlib>
+
 #include "ge_common.cuh"
 
 using namespace ge;
@@ -64,15 +66,23 @@ __device__ __forceinline__ void gather_add(const double *tab, int base, uint32_t
     }
 }
 
-template <int NWMAX>
-__global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NWP, int warp_bytes, int G) {
+// CSRP: sparse graphs (average degree <= 32, M < 65536) gather a node's predecessors / successors by walking its CSR
+// row from a 16-bit shared-memory copy and testing the neighbour's level -- ~6 instructions per neighbour with all
+// lanes busy -- instead of looping over the set bits of (row & level set) word by word, where a warp-divergent loop per
+// 32-bit word served one or two lanes at a time (ncu r02 first capture at N=500: 55 % of all instructions, 15 of 32
+// threads active).  The bit-matrix test stays as the cheap "does this node join the level at all" filter.  Dense graphs
+// keep the word loops (a complete graph has one level).
+template <int NWMAX, bool CSRP>
+__global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NWP, int warp_bytes, int G, int csr_bytes) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int b = blockIdx.x;
     const int N = d.N, NW = d.NW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5, tid = threadIdx.x, NT = blockDim.x;
     const int QN = NWP >> 2;
     uint32_t *mat = smem;
-    char *wbase = reinterpret_cast<char *>(mat + (size_t)N * NWP);
+    uint16_t *rp16 = reinterpret_cast<uint16_t *>(mat + (size_t)N * NWP);   // [N + 1] row offsets, [M] neighbour ids (CSRP)
+    uint16_t *col16 = rp16 + N + 1;
+    char *wbase = reinterpret_cast<char *>(mat + (size_t)N * NWP) + csr_bytes;
     double *sigma = reinterpret_cast<double *>(wbase + (size_t)warp * warp_bytes);
     double *delta = sigma + N;
     uint32_t *lv = reinterpret_cast<uint32_t *>(delta + N);
@@ -90,8 +100,11 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
         for (int e = lo + lane; e < hi; e += 32) {
             const int c = col[e];
             atomicOr(&mat[(size_t)u * NWP + (c >> 5)], 1u << (c & 31));
+            if (CSRP) col16[e] = (uint16_t)c;
         }
     }
+    if (CSRP)
+        for (int i = tid; i <= N; i += NT) rp16[i] = (uint16_t)rp[i];
     __syncthreads();
 
     // ---------------- betweenness + closeness: one search per source, one warp per source
@@ -122,6 +135,23 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
                 const uint4 *row = reinterpret_cast<const uint4 *>(mat + (size_t)v * NWP);
                 double sg = 0.0;
                 uint32_t q = quads;
+                if (CSRP) {
+                    uint32_t any = 0;
+                    while (q) {
+                        const int qi = __ffs(q) - 1;
+                        q &= q - 1;
+                        const uint4 r = row[qi];
+                        const uint4 l = reinterpret_cast<const uint4 *>(lv)[qi];
+                        any |= (r.x & l.x) | (r.y & l.y) | (r.z & l.z) | (r.w & l.w);
+                    }
+                    if (any) {
+                        const uint16_t want = (uint16_t)(level - 1);
+                        for (int e = rp16[v], hi = rp16[v + 1]; e < hi; ++e) {
+                            const int u = col16[e];
+                            if (D[u] == want) sg += sigma[u];
+                        }
+                    }
+                } else
                 while (q) {
                     const int qi = __ffs(q) - 1;
                     q &= q - 1;
@@ -173,15 +203,19 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
                 const bool in = dv == k;
                 if (in) sigma[v] = (1.0 + delta[v]) / sigma[v];
                 if (dv == k - 1) prev |= 1u << j;
-                const uint32_t wd = __ballot_sync(GE_FULL, in);
-                if (lane == j) myword = wd;
+                if (!CSRP) {
+                    const uint32_t wd = __ballot_sync(GE_FULL, in);
+                    if (lane == j) myword = wd;
+                }
             }
-            const uint32_t nz = __ballot_sync(GE_FULL, myword != 0u);
-            if (lane < NW) lv[lane] = myword;
             uint32_t qd = 0;
+            if (!CSRP) {
+                const uint32_t nz = __ballot_sync(GE_FULL, myword != 0u);
+                if (lane < NW) lv[lane] = myword;
 #pragma unroll
-            for (int qi = 0; qi < 8; ++qi)
-                if ((nz >> (4 * qi)) & 0xfu) qd |= 1u << qi;
+                for (int qi = 0; qi < 8; ++qi)
+                    if ((nz >> (4 * qi)) & 0xfu) qd |= 1u << qi;
+            }
             __syncwarp();
             while (prev) {
                 const int j = __ffs(prev) - 1;
@@ -189,7 +223,14 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
                 const int v = lane + (j << 5);
                 const uint4 *row = reinterpret_cast<const uint4 *>(mat + (size_t)v * NWP);
                 double acc = 0.0;
-                uint32_t q = qd;
+                if (CSRP) {
+                    const uint16_t want = (uint16_t)k;
+                    for (int e = rp16[v], hi = rp16[v + 1]; e < hi; ++e) {
+                        const int u = col16[e];
+                        if (D[u] == want) acc += sigma[u];           // coefficient of a successor
+                    }
+                }
+                uint32_t q = CSRP ? 0u : qd;
                 while (q) {
                     const int qi = __ffs(q) - 1;
                     q &= q - 1;
@@ -502,28 +543,40 @@ extern "C" int ge_features(const ge_batch *d, void *stream) {
     const int NWP = feat_nwp(NW), wb = feat_warp_bytes(N, NWP);
     const size_t mat_bytes = (size_t)N * NWP * 4;
     const size_t budget = 227 * 1024;
+    const int avg = N > 0 ? d->M / N : 1;
+    // sparse graphs: 16-bit CSR copy in shared memory for the predecessor / successor gathers
+    bool csrp = avg <= 32 && d->M < 65536 && !getenv("GE_FEAT_NO_CSR");
+    size_t csr_bytes = csrp ? (((size_t)2 * (N + 1) + (size_t)2 * d->M + 15) & ~(size_t)15) : 0;
+    if (csrp && mat_bytes + csr_bytes + 4 * (size_t)wb + 128 > budget) { csrp = false; csr_bytes = 0; }
     int W = (N + 7) / 8;                         // sources per warp >= 8 where there are that many
     if (W < 2) W = 2;                            // the pagerank overlay needs two warps' scratch
     if (W > 16) W = 16;
-    while (W > 2 && mat_bytes + (size_t)W * wb + 8 * 16 > budget) --W;
-    const size_t need = mat_bytes + (size_t)W * wb + 8 * 16;
+    while (W > 2 && mat_bytes + csr_bytes + (size_t)W * wb + 8 * 16 > budget) --W;
+    const size_t need = (size_t)W * wb + 8 * 16;
     const size_t overlay = 3 * (size_t)N * 8 + 8 * 16;           // x, y, invS, red[W]
-    size_t smem = mat_bytes + (need - mat_bytes > overlay ? need - mat_bytes : overlay);
+    size_t smem = mat_bytes + csr_bytes + (need > overlay ? need : overlay);
     if (smem > budget) return launch_warp_family(d, st);
-    const int avg = N > 0 ? d->M / N : 1;
     int G = 1;
     while (G < 32 && 2 * G <= avg / 2) G <<= 1;                   // lanes per CSR row in the pagerank mat-vec
     const void *kernel;
-    if (NW <= 2) kernel = (const void *)features_cta_kernel<2>;
-    else if (NW <= 4) kernel = (const void *)features_cta_kernel<4>;
-    else if (NW <= 8) kernel = (const void *)features_cta_kernel<8>;
-    else if (NW <= 16) kernel = (const void *)features_cta_kernel<16>;
-    else kernel = (const void *)features_cta_kernel<32>;
+    if (csrp) {
+        if (NW <= 2) kernel = (const void *)features_cta_kernel<2, true>;
+        else if (NW <= 4) kernel = (const void *)features_cta_kernel<4, true>;
+        else if (NW <= 8) kernel = (const void *)features_cta_kernel<8, true>;
+        else if (NW <= 16) kernel = (const void *)features_cta_kernel<16, true>;
+        else kernel = (const void *)features_cta_kernel<32, true>;
+    } else {
+        if (NW <= 2) kernel = (const void *)features_cta_kernel<2, false>;
+        else if (NW <= 4) kernel = (const void *)features_cta_kernel<4, false>;
+        else if (NW <= 8) kernel = (const void *)features_cta_kernel<8, false>;
+        else if (NW <= 16) kernel = (const void *)features_cta_kernel<16, false>;
+        else kernel = (const void *)features_cta_kernel<32, false>;
+    }
     int rc = ge_grant_smem(kernel, smem);
     if (rc) return rc;
     ge_batch dd = *d;
-    int nwp = NWP, wbytes = wb, g = G;
-    void *args[] = {&dd, &nwp, &wbytes, &g};
+    int nwp = NWP, wbytes = wb, g = G, cb = (int)csr_bytes;
+    void *args[] = {&dd, &nwp, &wbytes, &g, &cb};
     cudaError_t e = cudaLaunchKernel(kernel, dim3((unsigned)d->B), dim3((unsigned)(W * 32)), args, smem, st);
     if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "features_cta_kernel launch: %s", cudaGetErrorString(e));
     return GE_OK;

@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
             // `a` is valid => it IS the running-argmin edge of v, whose key holds float32(dist[src a] + delay[a]) in its
             // high word: the very value of :228, computed with the same float32 add when the edge was folded in.
             // No esrc[a] / dist[u] round trip (two scattered sectors).
-            dv = __uint_as_float((uint32_t)(reinterpret_cast<const u64 *>(d.bestkey)[(size_t)b * N + v] >> 32));
+            uint32_t hi32 = 0;                                              // lane 0 reads (it rewrites best[v] below), the group shares it
+            if (lane == 0) hi32 = (uint32_t)(reinterpret_cast<const u64 *>(d.bestkey)[(size_t)b * N + v] >> 32);
+            dv = __uint_as_float(g.shfl(hi32, 0));
         } else {
             const int u = d.esrc[(size_t)b * d.MP + a];
             dv = __fadd_rn(d.dist32[(size_t)b * N + u], w);                 // float32 add (:228)

@@ -201,6 +201,14 @@ int ge_generate(const ge_batch *batch, uint64_t seed, int32_t *row_ptr, int32_t 
  * emitted connected-by-construction instead; synchronises the stream.  Negative = error. */
 int ge_generate_fallbacks(void *stream);
 
+/* Instance turnover (every reference reset() builds a new graph): gives each env whose episode has ended (done[b] != 0) the
+ * next instance of its slot from a pool of `n_banks` prepared batches -- bank order[episode[b] % n_active], episode[b]++ --
+ * by copying that instance's static arrays over the env's own, and writes select[b] = 1 for those envs (0 for the others);
+ * follow with ge_reset(batch, select).  banks: HOST array of descriptors shaped like `batch`; order (int32[n_active]),
+ * episode (uint32[B]), select (uint8[B]): device arrays.  A bank that is being regenerated is left out of `order`. */
+int ge_pool_refill(const ge_batch *batch, const ge_batch *banks, int n_banks, const int32_t *order, int n_active,
+                   uint32_t *episode, uint8_t *select, void *stream);
+
 /* select: device uint8[B] (1 = reset this env) or NULL for all. */
 int ge_reset(const ge_batch *batch, const uint8_t *select, void *stream);
 int ge_step(const ge_batch *batch, const int32_t *actions, const ge_step_out *out, void *stream);

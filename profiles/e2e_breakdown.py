@@ -36,7 +36,8 @@ def graph_of(body):
             body()
 
     def run():
-        g.replay()
+        with torch.cuda.stream(side):      # replay() launches on the CURRENT stream
+            g.replay()
         side.synchronize()
     return run
 
@@ -52,7 +53,8 @@ out["d2h_bytes"] = int(io_dev.numel())
 env.sample_actions(3, 0)
 out["kernel_only_us"] = wall(graph_of(lambda: env.step_sampled(3, 0)))
 for name, kw in [("single", dict(pipelined=False)), ("pipelined_1", dict(pipelined=True, chunks=1)), ("pipelined_2", dict(pipelined=True, chunks=2)),
-                 ("pipelined_4", dict(pipelined=True, chunks=4)), ("pipelined_8", dict(pipelined=True, chunks=8))]:
+                 ("pipelined_3", dict(pipelined=True, chunks=3)), ("pipelined_4", dict(pipelined=True, chunks=4)),
+                 ("pipelined_6", dict(pipelined=True, chunks=6)), ("pipelined_8", dict(pipelined=True, chunks=8))]:
     stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, **kw)
 
     def one():

@@ -261,3 +261,74 @@ def test_spatial_tsp_generation_is_euclidean():
         u, v = ins.links[:, 0], ins.links[:, 1]
         dist = np.sqrt(((xy[b, u] - xy[b, v]) ** 2).sum(1))
         np.testing.assert_allclose(ins.w64, dist, rtol=1e-5)     # xy is stored as float32, the weight came from fp64 coordinates
+
+
+@pytest.mark.parametrize("cfg", [("ShortestPath-v0", 10, 20, {}), ("LongestPath-v0", 50, 200, {"parenting": 2}),
+                                 ("SteinerTree-v0", 40, 100, {"n_dests": 4}), ("TSP-v0", 100, 400, {"parenting": 1}),
+                                 ("DistributionCenter-v0", 100, 400, {"parenting": 2}), ("MulticastRouting-v0", 60, 200, {"n_dests": 3, "parenting": 4})],
+                         ids=lambda c: c[0][:-3])
+def test_instance_pool_gives_finished_envs_a_fresh_instance(cfg):
+    """Regenerate-on-done: after turn_over() every finished env carries an instance of a pool bank (bit-equal
+    arrays), is reset (done = 0, fresh mask), and the other envs are untouched; with background regeneration the banks
+    change over time.  The stepped trajectories stay valid (no invalid action statuses)."""
+    from graphenvs_b200.pool import InstancePool
+    env_id, N, E, kw = cfg
+    B = 300
+    env = BatchedGraphEnv(env_id, B, N, E, auto_reset=False, **kw)
+    env.generate(seed=1)
+    env.reset()
+    pool = InstancePool(env, banks=3, seed=7, background=False)
+    first_col = env.t["col"].clone()
+    seen_done = 0
+    for t in range(60):
+        env.step_sampled(5, t)
+        done = env.t["done"].clone().bool()
+        before = {k: env.t[k].clone() for k in ("col", "row_ptr", "node_bits", "mask_bits")}
+        ep_before = pool.episode.clone()
+        pool.turn_over()
+        torch.cuda.synchronize()
+        assert int(env.flags[:, 2].max()) == 0
+        assert not env.t["done"].any(), "every finished env has been reset"
+        assert torch.equal(pool.select.bool(), done)
+        for k, v in before.items():
+            assert torch.equal(env.t[k][~done], v[~done]), "%s of an unfinished env changed" % k
+        if done.any():
+            seen_done += int(done.sum())
+            idx = torch.nonzero(done).flatten()
+            bank_of = (ep_before[idx] % pool.n_active).cpu().tolist()
+            for i, k in zip(idx.cpu().tolist()[:20], bank_of[:20]):
+                bk = pool.banks[pool._host_order[k]]
+                assert torch.equal(env.t["col"][i], bk.t["col"][i]) and torch.equal(env.t["row_ptr"][i], bk.t["row_ptr"][i])
+            assert torch.equal(pool.episode[idx], ep_before[idx] + 1)
+    assert seen_done > B, "episodes must have turned over"
+    assert not torch.equal(env.t["col"], first_col)
+    # the refilled envs behave like freshly loaded ones: a twin batch loaded with the same instances agrees step for step
+    twin = BatchedGraphEnv(env_id, B, N, E, auto_reset=False, **kw)
+    twin.load_instances(env.export_instances())
+    twin.reset(select=torch.ones(B, dtype=torch.uint8))
+    env.reset()
+    for t in range(10):
+        a = env.sample_actions(9, t).clone()
+        env.step_async(a)
+        twin.step_async(a)
+    torch.cuda.synchronize()
+    assert torch.equal(env.t["mask_bits"], twin.t["mask_bits"]) and torch.equal(env.reward, twin.reward)
+
+
+def test_instance_pool_background_regeneration_swaps_banks():
+    from graphenvs_b200.pool import InstancePool
+    env = BatchedGraphEnv("ShortestPath-v0", 2048, 10, 20, auto_reset=False)
+    env.generate(seed=1)
+    env.reset()
+    pool = InstancePool(env, banks=3, seed=3, background=True)
+    snap = [b.t["col"].clone() for b in pool.banks]
+    for t in range(400):
+        env.step_sampled(5, t)
+        pool.turn_over()
+        if t % 50 == 0:
+            torch.cuda.synchronize()
+    pool.close()
+    torch.cuda.synchronize()
+    assert pool.regenerated >= 1, "the background stream must have delivered at least one new bank"
+    assert sum(int(not torch.equal(s, b.t["col"])) for s, b in zip(snap, pool.banks)) >= 1
+    assert int(env.flags[:, 2].max()) == 0
