@@ -400,7 +400,7 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
     torch.cuda.synchronize()
     Ke = max(3, min(K, args.e2e_steps))
     side = torch.cuda.Stream(device=dev)       # a real stream: ge_step_host replays its copy/step/copy sequence as a graph
-    stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"))
+    stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"), chunks=args.e2e_chunks)
     e2e_s = 0.0
     D.barrier()
     for k in range(3 + Ke):
@@ -475,7 +475,7 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
                 "timed": ("sum of ge_step_host calls: pinned H2D actions, step kernel, D2H of reward/flags/solution_cost/packed mask, "
-                          "stream sync (%s); policy between calls untimed" % args.e2e)},
+                          "completion wait (%s%s); policy between calls untimed" % (args.e2e, ", %d slices" % args.e2e_chunks if args.e2e == "pipelined" else ""))},
         "e2e_obs": e2e_obs,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
@@ -682,6 +682,7 @@ def main():
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
     ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],
                     help="pipelined: ge_step_host in chunks on two streams (copies overlap kernels); single: one copy-in / kernel / copy-out")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the pipelined end-to-end step")
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")
     args = ap.parse_args()

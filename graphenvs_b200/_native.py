@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed for %s" % ", ".join(os.path.basename(f) for f in failed))
     open(tag, "w").write(flag_sig)
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs, env=env)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-ldl"], env=env)
     return LIB_PATH
 
 

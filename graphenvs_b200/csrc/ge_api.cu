@@ -529,6 +529,7 @@ int ge_fill_layout(ge_batch *d) {
 int ge_step_smem_bytes(const ge_batch *d) { return scratch_words(*d) * GE_WPB * (int)sizeof(uint32_t); }
 
 int ge_build_adjacency(const ge_batch *d, void *stream) {
+    GE_NVTX("ge_build_adjacency");
     int rc = check_batch(d);
     if (rc) return rc;
     if (!d->adj_bits && !d->rev && !d->esrc && !d->wmin) return fail(GE_ERR_ARG, "no derived array requested (adj_bits / rev / esrc / wmin are null)");
@@ -538,6 +539,7 @@ int ge_build_adjacency(const ge_batch *d, void *stream) {
 }
 
 int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
+    GE_NVTX("ge_prepare");
     int rc = check_batch(d);
     if (rc) return rc;
     int blocks, wpw;
@@ -587,6 +589,7 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
 }
 
 int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
+    GE_NVTX("ge_reset");
     int rc = check_batch(d);
     if (rc) return rc;
     if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
@@ -627,14 +630,17 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
 }
 
 int ge_step(const ge_batch *d, const int32_t *actions, const ge_step_out *out, void *stream) {
+    GE_NVTX("ge_step");
     return step_impl(d, const_cast<int32_t *>(actions), out, false, 0, 0, stream);  // not written when !sampled
 }
 
 int ge_step_sampled(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, const ge_step_out *out, void *stream) {
+    GE_NVTX("ge_step_sampled");
     return step_impl(d, actions, out, true, seed, t, stream);
 }
 
 int ge_sample_actions(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *actions, void *stream) {
+    GE_NVTX("ge_sample_actions");
     int rc = check_batch(d);
     if (rc) return rc;
     if (d->AW <= 2) return ge_lane_sample(d, seed, t, actions, (cudaStream_t)stream);
@@ -650,6 +656,7 @@ int ge_obs_len(const ge_batch *d) {
 }
 
 int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stream) {
+    GE_NVTX("ge_obs_flat");
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
@@ -659,6 +666,7 @@ int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stre
 }
 
 int ge_obs_graph(const ge_batch *d, int env_lo, int count, float *x, float *edge_attr, int64_t *edge_index, void *stream) {
+    GE_NVTX("ge_obs_graph");
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
@@ -669,6 +677,7 @@ int ge_obs_graph(const ge_batch *d, int env_lo, int count, float *x, float *edge
 }
 
 int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *stream) {
+    GE_NVTX("ge_obs_nodes");
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
@@ -683,6 +692,7 @@ int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(
 int ge_mask_bytes_current(const ge_batch *d) { return d && d->mask_bytes && !ge_incr_eligible(d); }
 
 int ge_mask_bytes(const ge_batch *d, int env_lo, int count, void *stream) {
+    GE_NVTX("ge_mask_bytes");
     int rc = check_batch(d);
     if (rc) return rc;
     if (!d->mask_bytes) return fail(GE_ERR_ARG, "byte mask not enabled");
@@ -812,6 +822,14 @@ __global__ void __launch_bounds__(256) writeback_kernel(const float *reward, con
 }
 }  // namespace
 
+// GE_PIPE_ZC=1: the step kernels read the actions straight from the caller's pinned host buffer (coalesced PCIe reads) and
+// the copy-in lane disappears; GE_HOST_SPIN=1: ge_step_host also polls for completion instead of a blocking synchronize.
+static bool env_flag(const char *name, int *cache) {
+    if (*cache < 0) { const char *e = getenv(name); *cache = (e && e[0] != '0') ? 1 : 0; }
+    return *cache == 1;
+}
+static int g_pipe_zc = -1, g_host_spin = -1;
+
 int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     if (!d || !o) return fail(GE_ERR_ARG, "null batch");
     if (lo < 0 || count <= 0 || lo + count > d->B || (lo & 31)) return fail(GE_ERR_ARG, "bad slice [%d, %d) of %d envs (lo must be a multiple of 32)", lo, lo + count, d->B);
@@ -842,6 +860,7 @@ int ge_step_host_release(const ge_batch *d) {
 
 int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                  ge_step_flags *h_flags, double *h_solution_cost, uint8_t *h_mask, uint32_t *h_mask_bits, void *stream) {
+    GE_NVTX("ge_step_host");
     cudaStream_t st = (cudaStream_t)stream;
     if (!d) return fail(GE_ERR_ARG, "null batch");
     const size_t B = (size_t)d->B;
@@ -872,7 +891,8 @@ int ge_step_host(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions
         }
         if (exec) {
             GE_CUDA_OK(cudaGraphLaunch(exec, st));
-            GE_CUDA_OK(cudaStreamSynchronize(st));
+            if (env_flag("GE_HOST_SPIN", &g_host_spin)) GE_CUDA_OK(spin_until_done(st));
+            else GE_CUDA_OK(cudaStreamSynchronize(st));
             return GE_OK;
         }
         // first call for this (descriptor, buffers, stream): run once directly (also sets kernel attributes), then capture
@@ -907,7 +927,7 @@ static int pipelined_copy_in(const ge_batch *d, int lo, int n, const int32_t *h_
     GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     return GE_OK;
 }
-static int pipelined_step(const ge_batch *d, int lo, int n, int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
+static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
     ge_batch sl;
     int rc = ge_batch_slice(d, lo, n, &sl);
     if (rc) return rc;
@@ -929,6 +949,7 @@ static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_
 
 int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                            ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits, int chunks, void *stream) {
+    GE_NVTX("ge_step_host_pipelined");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_batch(d);
     if (rc) return rc;
@@ -947,10 +968,12 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
     if (!exec) {
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
         // three-lane sequence for the following calls
+        const bool zc = env_flag("GE_PIPE_ZC", &g_pipe_zc);
+        const int32_t *acts = zc ? h_actions : d_actions;
         for (int i = 0; i < chunks; ++i) {
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
-            if ((rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
-            if ((rc = pipelined_step(d, lo, n, d_actions, out, st))) return rc;
+            if (!zc && (rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
+            if ((rc = pipelined_step(d, lo, n, acts, out, st))) return rc;
             if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
@@ -973,13 +996,15 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc2 = GE_OK;
             cudaStream_t s_in = g_side[0], s_out = g_side[1];
-            bool ok = cudaEventRecord(g_fork, st) == cudaSuccess && cudaStreamWaitEvent(s_in, g_fork, 0) == cudaSuccess &&
+            bool ok = cudaEventRecord(g_fork, st) == cudaSuccess && (zc || cudaStreamWaitEvent(s_in, g_fork, 0) == cudaSuccess) &&
                       cudaStreamWaitEvent(s_out, g_fork, 0) == cudaSuccess;
             for (int i = 0; ok && i < chunks && rc2 == GE_OK; ++i) {
                 const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
-                rc2 = pipelined_copy_in(d, lo, n, h_actions, d_actions, s_in);
-                ok = ok && cudaEventRecord(g_in[i], s_in) == cudaSuccess && cudaStreamWaitEvent(st, g_in[i], 0) == cudaSuccess;
-                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, d_actions, out, st);
+                if (!zc) {
+                    rc2 = pipelined_copy_in(d, lo, n, h_actions, d_actions, s_in);
+                    ok = ok && cudaEventRecord(g_in[i], s_in) == cudaSuccess && cudaStreamWaitEvent(st, g_in[i], 0) == cudaSuccess;
+                }
+                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, out, st);
                 ok = ok && cudaEventRecord(g_stepped[i], st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_stepped[i], 0) == cudaSuccess;
                 if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s_out);
             }
@@ -1002,6 +1027,7 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
 }
 
 int ge_stats(const ge_batch *d, double *out4, void *stream) {
+    GE_NVTX("ge_stats");
     int rc = check_batch(d);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;

@@ -12,6 +12,19 @@
 
 #include "graphenvs_b200.h"
 
+#ifndef __CUDA_ARCH__
+#include <nvtx3/nvToolsExt.h>
+// NVTX range around a C-ABI entry point (SURVEY section 5 "tracing / profiling"): visible in Nsight Systems timelines,
+// a few nanoseconds when no tool is attached.
+struct GeNvtxRange {
+    explicit GeNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~GeNvtxRange() { nvtxRangePop(); }
+};
+#define GE_NVTX(name) GeNvtxRange _ge_nvtx_range(name)
+#else
+#define GE_NVTX(name)
+#endif
+
 #define GE_FULL 0xffffffffu
 #define GE_WPB 8  // warps (= environments) per thread block
 

@@ -58,6 +58,26 @@ __device__ __forceinline__ double block_sum(double v, double *red, int W) {
     return t;
 }
 
+// sum of tab[u] over the neighbours u of row [lo, hi) whose level is `want`: four neighbours per trip so that the
+// level and value loads of a trip are independent (the plain loop was a chain of three dependent shared-memory loads
+// per neighbour at four warps per scheduler)
+__device__ __forceinline__ double csr_gather(const uint16_t *col16, const uint16_t *D, const double *tab, int lo, int hi, uint16_t want) {
+    double a0 = 0.0, a1 = 0.0;
+    int e = lo;
+    for (; e + 4 <= hi; e += 4) {
+        const int u0 = col16[e], u1 = col16[e + 1], u2 = col16[e + 2], u3 = col16[e + 3];
+        const bool p0 = D[u0] == want, p1 = D[u1] == want, p2 = D[u2] == want, p3 = D[u3] == want;
+        const double s0 = p0 ? tab[u0] : 0.0, s1 = p1 ? tab[u1] : 0.0, s2 = p2 ? tab[u2] : 0.0, s3 = p3 ? tab[u3] : 0.0;
+        a0 += s0 + s2;
+        a1 += s1 + s3;
+    }
+    for (; e < hi; ++e) {
+        const int u = col16[e];
+        if (D[u] == want) a0 += tab[u];
+    }
+    return a0 + a1;
+}
+
 // sum of tab[base + i] over the set bits i of x
 __device__ __forceinline__ void gather_add(const double *tab, int base, uint32_t x, double &acc) {
     while (x) {
@@ -144,13 +164,7 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
                         const uint4 l = reinterpret_cast<const uint4 *>(lv)[qi];
                         any |= (r.x & l.x) | (r.y & l.y) | (r.z & l.z) | (r.w & l.w);
                     }
-                    if (any) {
-                        const uint16_t want = (uint16_t)(level - 1);
-                        for (int e = rp16[v], hi = rp16[v + 1]; e < hi; ++e) {
-                            const int u = col16[e];
-                            if (D[u] == want) sg += sigma[u];
-                        }
-                    }
+                    if (any) sg = csr_gather(col16, D, sigma, rp16[v], rp16[v + 1], (uint16_t)(level - 1));
                 } else
                 while (q) {
                     const int qi = __ffs(q) - 1;
@@ -223,13 +237,7 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
                 const int v = lane + (j << 5);
                 const uint4 *row = reinterpret_cast<const uint4 *>(mat + (size_t)v * NWP);
                 double acc = 0.0;
-                if (CSRP) {
-                    const uint16_t want = (uint16_t)k;
-                    for (int e = rp16[v], hi = rp16[v + 1]; e < hi; ++e) {
-                        const int u = col16[e];
-                        if (D[u] == want) acc += sigma[u];           // coefficient of a successor
-                    }
-                }
+                if (CSRP) acc = csr_gather(col16, D, sigma, rp16[v], rp16[v + 1], (uint16_t)k);   // coefficients of the successors
                 uint32_t q = CSRP ? 0u : qd;
                 while (q) {
                     const int qi = __ffs(q) - 1;
@@ -536,6 +544,7 @@ static int launch_warp_family(const ge_batch *d, cudaStream_t st) {
 }  // namespace
 
 extern "C" int ge_features(const ge_batch *d, void *stream) {
+    GE_NVTX("ge_features");
     if (!d || !d->features) return ge_set_error(GE_ERR_ARG, "ge_features: features buffer is null");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = d->N, NW = d->NW;

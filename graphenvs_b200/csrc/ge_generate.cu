@@ -311,6 +311,7 @@ __global__ void clear_fallbacks_kernel() { g_generate_fallbacks = 0; }
 }  // namespace
 
 extern "C" int ge_generate(const ge_batch *d, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32, void *stream) {
+    GE_NVTX("ge_generate");
     if (!d || !row_ptr || !col) return ge_set_error(GE_ERR_ARG, "ge_generate: null buffers");
     if (d->N > 1024) return ge_set_error(GE_ERR_UNSUPPORTED, "ge_generate: N=%d > 1024 (bit-matrix must fit one warp's shared-memory slice)", d->N);
     const int E = d->M / 2;

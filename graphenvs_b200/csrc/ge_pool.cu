@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) pool_refill_kernel(ge_batch d, PoolTab ta
 // now.  episode: DEVICE uint32[B] per-env episode counter.  select: DEVICE uint8[B], written for every env (1 = refilled).
 extern "C" int ge_pool_refill(const ge_batch *live, const ge_batch *banks, int n_banks, const int32_t *order, int n_active,
                               uint32_t *episode, uint8_t *select, void *stream) {
+    GE_NVTX("ge_pool_refill");
     if (!live || !banks || !order || !episode || !select) return ge_set_error(GE_ERR_ARG, "ge_pool_refill: null argument");
     if (n_banks < 1 || n_banks > POOL_MAX_BANKS || n_active < 1 || n_active > n_banks) return ge_set_error(GE_ERR_ARG, "ge_pool_refill: 1 <= n_active <= n_banks <= %d", POOL_MAX_BANKS);
     PoolTab tab;

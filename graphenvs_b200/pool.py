@@ -22,6 +22,7 @@ class InstancePool:
         self.env, self.G, self.seed = env, int(banks), int(seed)
         P = dict(env.params)
         n_nodes, n_edges = P.pop("n_nodes"), P.pop("n_edges")
+        P.pop("structural_features", None)          # ShortestPath's ignored ctor kwarg (shortest_path.py:23) vs the engine's own flag
         self.banks = []
         for k in range(self.G):
             b = BatchedGraphEnv(env.env_id, env.B, n_nodes, n_edges, device=env.device, byte_mask=False, auto_reset="mask0_bits" in env.t,
