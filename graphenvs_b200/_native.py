@@ -82,7 +82,7 @@ class GeBatch(C.Structure):
         ("NW", C.c_int32), ("MW", C.c_int32), ("A", C.c_int32), ("AW", C.c_int32), ("AP", C.c_int32),
         ("RP", C.c_int32), ("MP", C.c_int32), ("ADJS", C.c_int32), ("acc_stride", C.c_int32), ("dfa_bytes", C.c_int32),
         ("max_distance", C.c_double),
-        ("row_ptr", _P), ("col", _P), ("w32", _P), ("w64", _P), ("adj_bits", _P), ("rev", _P), ("esrc", _P), ("wsort", _P), ("wcode", _P), ("dfa", _P), ("wmin", _P), ("wmat", _P),
+        ("row_ptr", _P), ("col", _P), ("w32", _P), ("w64", _P), ("adj_bits", _P), ("rev", _P), ("esrc", _P), ("wsort", _P), ("wcode", _P), ("dfa", _P), ("dc_edges", _P), ("wmin", _P), ("wmat", _P),
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
         ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("heuristic", _P), ("heuristic_alt", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P), ("bestkey", _P),

@@ -14,7 +14,7 @@ import torch
 from . import _native
 from .spec import ENV_SPECS, check_ctor_args
 
-PREP_HEURISTIC, PREP_MAXDIST, PREP_INRANGE, PREP_ALT_HEURISTIC = 1, 2, 4, 8
+PREP_HEURISTIC, PREP_MAXDIST, PREP_INRANGE, PREP_ALT_HEURISTIC, PREP_DC_EDGES = 1, 2, 4, 8, 16
 
 
 def _ptr(t):
@@ -134,7 +134,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "dc_edges", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
@@ -248,6 +248,8 @@ class BatchedGraphEnv:
         what = 0
         if prepare and self.env_id == "DistributionCenter-v0" and d.parenting == 2:
             what |= PREP_INRANGE
+        if "dc_edges" in self.t:
+            what |= PREP_DC_EDGES
         if heuristics and self.spec.heuristic_on_device(self.params):
             what |= PREP_HEURISTIC
         if self.is_eval_env and "heuristic_alt" in self.t and ("w64" in self.t or self.env_id == "MaxIndependentSet-v0"):
@@ -267,7 +269,7 @@ class BatchedGraphEnv:
         every edge weight of the batch is one of <= 15 distinct doubles (k/10 in the reference) and the closure of
         left-fold sums within the cutoff has < 255 values; otherwise the fp64 search stays in charge."""
         T, d, B, M = self.t, self.desc, self.B, self.M
-        for k in ("wcode", "dfa"):
+        for k in ("wcode", "dfa", "dc_edges"):
             T.pop(k, None)
         self._sync_desc()
         self.desc.dfa_bytes = 0
@@ -298,6 +300,9 @@ class BatchedGraphEnv:
                 if s + x <= cutoff:
                     tab[i, j] = idx[s + x]
         expand = np.array([1 if s + ws[0] <= cutoff else 0 for s in st], dtype=np.uint8)
+        cmax = np.array([max([j for j in range(W) if tab[i, j] != 255], default=255) for i in range(S)], dtype=np.uint8)
+        for i in range(S):          # fl(value + weight) is monotone in the weight: the usable codes of a state are a prefix
+            assert all(tab[i, j] != 255 for j in range(0 if cmax[i] == 255 else cmax[i] + 1))
         code = torch.zeros((B, d.MP), dtype=torch.uint8, device=self.device)
         step = max(1, (64 << 20) // max(M, 1))
         for lo in range(0, B, step):
@@ -307,7 +312,9 @@ class BatchedGraphEnv:
                 return False                                           # a weight outside the sampled set: keep fp64
             code[lo:lo + step, :M] = c.to(torch.uint8)
         T["wcode"] = code
-        T["dfa"] = torch.from_numpy(np.concatenate([np.array([S, W], dtype=np.uint8), tab.ravel(), expand])).to(self.device)
+        T["dfa"] = torch.from_numpy(np.concatenate([np.array([S, W], dtype=np.uint8), tab.ravel(), expand, cmax])).to(self.device)
+        if self.N <= 1024 and self.N < 65536:
+            T["dc_edges"] = torch.zeros((B, d.MP), dtype=torch.int32, device=self.device)   # weight-sorted rows for csrc/ge_dc.cu
         self._sync_desc()
         self.desc.dfa_bytes = int(T["dfa"].numel())
         return True

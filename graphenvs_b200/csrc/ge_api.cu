@@ -456,6 +456,7 @@ int ge_incr_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 bool ge_dc_eligible(const ge_batch *d);
 int ge_dc_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_dc_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
+int ge_dc_build_edges(const ge_batch *d, cudaStream_t st);
 // eval heuristic kernels (ge_heuristics.cu)
 int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
@@ -574,6 +575,9 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
         if ((rc = set_smem(prep_sssp_kernel, smem))) return rc;
         prep_sssp_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, 2, u01, wpw);
         GE_CUDA_OK(cudaGetLastError());
+    }
+    if ((what & 16) && d->kind == GE_DISTRIBUTION_CENTER) {
+        if ((rc = ge_dc_build_edges(d, st))) return rc;
     }
     if ((what & 4) && d->kind == GE_DISTRIBUTION_CENTER && d->n_targets > 0) {
         if (!d->w64) return fail(GE_ERR_ARG, "in-range tables need w64");
@@ -822,10 +826,12 @@ __global__ void __launch_bounds__(256) writeback_kernel(const float *reward, con
 }
 }  // namespace
 
-// GE_PIPE_ZC=1: the step kernels read the actions straight from the caller's pinned host buffer (coalesced PCIe reads) and
-// the copy-in lane disappears; GE_HOST_SPIN=1: ge_step_host also polls for completion instead of a blocking synchronize.
-static bool env_flag(const char *name, int *cache) {
-    if (*cache < 0) { const char *e = getenv(name); *cache = (e && e[0] != '0') ? 1 : 0; }
+// GE_PIPE_ZC (default on): the step kernels of ge_step_host_pipelined read the actions straight from the caller's pinned
+// host buffer (coalesced PCIe reads) and the copy-in lane disappears -- measured 59.2 -> 53.0 us per 65,536-env step at two
+// slices (profiles/r02_e2e_breakdown.jsonl); GE_PIPE_ZC=0 restores the H2D copies.  GE_HOST_SPIN=1: ge_step_host also polls
+// for completion instead of a blocking synchronize (no measurable difference on the test boxes).
+static bool env_flag(const char *name, int *cache, bool dflt = false) {
+    if (*cache < 0) { const char *e = getenv(name); *cache = e ? (e[0] != '0' ? 1 : 0) : (dflt ? 1 : 0); }
     return *cache == 1;
 }
 static int g_pipe_zc = -1, g_host_spin = -1;
@@ -840,7 +846,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
 #define ADV(field, per_env) if (d->field) o->field = d->field + b * (size_t)(per_env)
     ADV(row_ptr, d->RP); ADV(col, d->MP); ADV(w32, d->MP); ADV(w64, d->MP);
     if (d->adj_bits) o->adj_bits = d->adj_bits + (adj_tiled(*d) ? (b >> 5) * (size_t)d->N * 32 * d->NW : b * (size_t)d->ADJS);
-    ADV(rev, d->MP); ADV(esrc, d->MP); ADV(wsort, d->MP); ADV(wcode, d->MP); ADV(wmin, 1); ADV(wmat, (size_t)d->N * d->N);
+    ADV(rev, d->MP); ADV(esrc, d->MP); ADV(wsort, d->MP); ADV(wcode, d->MP); ADV(dc_edges, d->MP); ADV(wmin, 1); ADV(wmat, (size_t)d->N * d->N);
     ADV(src, 1); ADV(dest, 1); ADV(target_bits, d->NW); ADV(node_cost, d->N); ADV(node_xy, 2 * d->N); ADV(max_dist32, 1);
     ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(heuristic, 1); ADV(heuristic_alt, 1); ADV(features, 5 * d->N);
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
@@ -968,7 +974,7 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
     if (!exec) {
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
         // three-lane sequence for the following calls
-        const bool zc = env_flag("GE_PIPE_ZC", &g_pipe_zc);
+        const bool zc = env_flag("GE_PIPE_ZC", &g_pipe_zc, true);
         const int32_t *acts = zc ? h_actions : d_actions;
         for (int i = 0; i < chunks; ++i) {
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;

@@ -9,9 +9,10 @@
 //   * node sets (taken, covered, targets, mask) live in REGISTERS, lane w owns word w; set algebra is one instruction,
 //     membership of an arbitrary node is one shuffle;
 //   * the cutoff search (find_nodes_in_range = nx single_source_dijkstra_path_length(cutoff), label-correcting on the
-//     exact automaton, see ge_common.cuh:sssp_cutoff_dfa) walks the frontier LIST with a group of 16 lanes per row, two
-//     rows per trip (a row is ~16 edges): no scan, no owner search; the next pair's row bounds are loaded one trip
-//     ahead; the automaton's transition table sits in shared memory (one copy per block);
+//     exact automaton, see ge_common.cuh:sssp_cutoff_dfa) walks the frontier LIST with a group of 8 lanes per row, four
+//     rows per trip, over WEIGHT-SORTED rows of which only the prefix that can stay within the cutoff is visited: no
+//     scan, no owner search; the next rows' bounds are loaded one trip ahead; the automaton's tables sit in shared
+//     memory (one copy per block);
 //   * distances are automaton state ids in a per-warp shared array (native 32-bit atomicMin);
 //   * the mask is the OR of the in-range rows of the still uncovered targets, rows fetched 32/L at a time by groups
 //     of L >= NW lanes, four passes in flight.
@@ -27,7 +28,7 @@ int ge_grant_smem(const void *kernel, size_t smem);  // ge_api.cu
 
 namespace {
 
-__host__ __device__ inline int dc_dfa_words(const ge_batch &d, int S, int W) { return ((2 + S * W + S + 15) & ~15) >> 2; }
+__host__ __device__ inline int dc_dfa_words(const ge_batch &d, int S, int W) { return ((2 + S * W + 2 * S + 15) & ~15) >> 2; }
 __host__ __device__ inline int dc_warp_words(const ge_batch &d) { return ((d.N + d.N + 2 * d.NW + 4) + 3) & ~3; }  // q[N] | two u16 lists | reach, queued | counter
 
 struct DcScr {
@@ -49,8 +50,16 @@ __device__ __forceinline__ DcScr dc_carve(uint32_t *base, const ge_batch &d) {
 }
 
 // find_nodes_in_range(a): leaves the reached set in s.reach (shared, NW words).
-__device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
-                                                 const uint8_t *__restrict__ wc, const uint8_t *tab, const uint8_t *expand, int W,
+//
+// The rows are read from ge_batch.dc_edges: every row sorted by WEIGHT (code ascending), entry = col | code << 16.  A node
+// at automaton state du can only relax edges whose weight keeps the sum within the cutoff, and those form a PREFIX of its
+// weight-sorted row (cmax[du] = the largest such code; fl(dist + w) is monotone in w): with cutoff 1.0 and weights
+// 0.3..0.9 a node at distance 0.6 uses 2/7 of its edges.  Skipping the rest is exact -- they would have been looked up as
+// "beyond the cutoff" and dropped.  Eight lanes per row, four rows per trip; a row continues with another pass of eight
+// while its last lane was still inside the prefix.  (The first version walked whole rows, 16 lanes per row: 430 edge
+// visits per step where ~175 can matter; profiles/r02_dc_step_kernel_v1.md.)
+__device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_t *__restrict__ rp, const uint32_t *__restrict__ edges,
+                                                 const uint8_t *tab, const uint8_t *expand, const uint8_t *cmax, int W,
                                                  DcScr &s, int lane, int source) {
     const int N = d.N, NW = d.NW;
     {   // q[v] = 255
@@ -63,21 +72,25 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
     if (lane == 0) { s.q[source] = 0u; s.reach[source >> 5] = 1u << (source & 31); s.cur[0] = (uint16_t)source; *s.cnt = 0; }
     __syncwarp();
     int ncur = expand[0] ? 1 : 0;
-    const int grp = lane >> 4, gl = lane & 15;
+    const int grp = lane >> 3, gl = lane & 7;
     uint16_t *cur = s.cur, *nxt = s.nxt;
     while (ncur > 0) {
-        // bounds of the first pair
-        int lo = 0, hi = 0, du = 0;
+        int lo = 0, hi = 0, du = 0;                                     // bounds of the first four rows
         if (grp < ncur) { const int u = cur[grp]; lo = rp[u]; hi = rp[u + 1]; du = (int)s.q[u]; }
-        for (int i0 = 0; i0 < ncur; i0 += 2) {
-            int lo_n = 0, hi_n = 0, du_n = 0;                          // next pair, loaded while this one is relaxed
-            if (i0 + 2 + grp < ncur) { const int u = cur[i0 + 2 + grp]; lo_n = rp[u]; hi_n = rp[u + 1]; du_n = (int)s.q[u]; }
+        for (int i0 = 0; i0 < ncur; i0 += 4) {
+            int lo_n = 0, hi_n = 0, du_n = 0;                          // next four rows, loaded while these are relaxed
+            if (i0 + 4 + grp < ncur) { const int u = cur[i0 + 4 + grp]; lo_n = rp[u]; hi_n = rp[u + 1]; du_n = (int)s.q[u]; }
             const uint8_t *trow = tab + du * W;
-            for (int e = lo + gl; __any_sync(GE_FULL, e < hi); e += 16) {
-                if (e < hi) {
-                    const int v = col[e];
-                    const uint32_t nid = trow[wc[e]];                   // state of fl(dist + w), 255 = beyond the cutoff
-                    if (nid != 255u && nid < s.q[v]) {
+            const uint32_t cm = hi > lo ? (uint32_t)cmax[du] : 0u;      // 255 = nothing within the cutoff (never queued, but harmless)
+            for (int e = lo + gl;; e += 8) {
+                uint32_t pk = 0xffffffffu;
+                if (e < hi) pk = edges[e];
+                const uint32_t code = pk >> 16;
+                const bool act = e < hi && cm != 255u && code <= cm;
+                if (act) {
+                    const int v = (int)(pk & 0xffffu);
+                    const uint32_t nid = trow[code];                    // state of fl(dist + w); inside the prefix => never 255
+                    if (nid < s.q[v]) {
                         const uint32_t old = atomicMin(&s.q[v], nid);
                         if (nid < old) {
                             const uint32_t bit = 1u << (v & 31);
@@ -89,6 +102,7 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
                         }
                     }
                 }
+                if (!__any_sync(GE_FULL, act && gl == 7)) break;        // no row filled its whole pass: every prefix is exhausted
             }
             lo = lo_n; hi = hi_n; du = du_n;
         }
@@ -171,12 +185,12 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
     const int S = d.dfa[0], W = d.dfa[1];
     {   // automaton tables: one copy per block
         uint8_t *dst = reinterpret_cast<uint8_t *>(smem);
-        const int nbytes = 2 + S * W + S;
+        const int nbytes = 2 + S * W + 2 * S;
         for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = d.dfa[i];
     }
     __syncthreads();
     if (b >= d.B) return;
-    const uint8_t *tab = reinterpret_cast<const uint8_t *>(smem) + 2, *expand = tab + S * W;
+    const uint8_t *tab = reinterpret_cast<const uint8_t *>(smem) + 2, *expand = tab + S * W, *cmax = expand + S;
     DcScr s = dc_carve(smem + dfa_words + (size_t)warp * warp_words, d);
     const int N = d.N, NW = d.NW;
     const bool WL = lane < NW;
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
         cost = (double)__fadd_rn((float)cost, w);
         float rew = -w;
         if (lane == (a >> 5)) takenw |= 1u << (a & 31);
-        dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.col + (size_t)b * d.MP, d.wcode + (size_t)b * d.MP, tab, expand, W, s, lane, a);
+        dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, tab, expand, cmax, W, s, lane, a);
         const uint32_t reachw = WL ? s.reach[lane] : 0u;                          // find_nodes_in_range (:25-26,155)
         const int gained = __reduce_add_sync(GE_FULL, __popc(reachw & ~covw & tgtw));
         covw |= reachw;
@@ -301,14 +315,39 @@ __global__ void __launch_bounds__(GE_WPB * 32) dc_reset_kernel(ge_batch d, const
     }
 }
 
+// dc_edges: every CSR row re-ordered by weight code (stable), entry = col | code << 16.  One lane per row (rows are short;
+// reset-time code): count per code, then place.
+__global__ void __launch_bounds__(256) dc_edges_kernel(ge_batch d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)d.B * d.N) return;
+    const int b = (int)(i / d.N), u = (int)(i % d.N);
+    const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
+    const int32_t *col = d.col + (size_t)b * d.MP;
+    const uint8_t *wc = d.wcode + (size_t)b * d.MP;
+    uint32_t *out = d.dc_edges + (size_t)b * d.MP;
+    const int lo = rp[u], hi = rp[u + 1];
+    int pos = lo;
+    for (int c = 0; c < 16 && pos < hi; ++c)                       // at most 15 distinct weights (batch.py:_build_distance_automaton)
+        for (int e = lo; e < hi; ++e)
+            if (wc[e] == c) out[pos++] = (uint32_t)col[e] | ((uint32_t)c << 16);
+}
+
 }  // namespace
+
+int ge_dc_build_edges(const ge_batch *d, cudaStream_t st) {
+    if (!d->dc_edges || !d->wcode) return GE_OK;
+    const long long rows = (long long)d->B * d->N;
+    dc_edges_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(*d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "dc_edges_kernel launch: %s", cudaGetErrorString(e));
+}
 
 // ------------------------------------------------------------------ host launchers (called from ge_api.cu)
 bool ge_dc_eligible(const ge_batch *d) {
     static int off = -1;                                   // GE_NO_DC=1: A/B runs against the general warp-per-env kernel
     if (off < 0) off = getenv("GE_NO_DC") ? 1 : 0;
     if (off || (d->flags & GE_FLAG_FORCE_WARP)) return false;
-    if (d->kind != GE_DISTRIBUTION_CENTER || d->N > 1024 || !d->wcode || !d->dfa) return false;
+    if (d->kind != GE_DISTRIBUTION_CENTER || d->N > 1024 || !d->wcode || !d->dfa || !d->dc_edges) return false;
     if (d->parenting == 2 && (!d->in_range || !d->targets || d->n_targets > 1024 || d->n_targets > d->N)) return false;
     return d->node_bits2 != nullptr && d->target_bits != nullptr;
 }

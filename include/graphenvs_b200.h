@@ -110,12 +110,16 @@ typedef struct ge_batch {
     double *wsort;                /* [B, MP]   w64 permuted so that every row is in ascending destination order (derived), or
                                               NULL: adj[u, v] = wsort[row_ptr[u] + rank of v in the adjacency bit-row of u] */
     const uint8_t *wcode;         /* [B, MP]   index of every edge weight in the batch's small set of distinct weights, or NULL */
-    const uint8_t *dfa;           /* exact fp64 distance automaton for the cutoff SSSP, or NULL: [S, W, T[S*W], expand[S]].
+    const uint8_t *dfa;           /* exact fp64 distance automaton for the cutoff SSSP, or NULL: [S, W, T[S*W], expand[S], cmax[S]]
+                                              (cmax[i] = largest weight code j with T[i*W+j] != 255, or 255).
                                               State i = the i-th smallest value reachable as a left-fold fp64 sum of the W
                                               distinct weights without exceeding max_distance; T[i*W+j] = state of
                                               fl(value_i + weight_j) or 255 when it exceeds the cutoff; expand[i] = value_i +
                                               smallest weight <= cutoff.  Built on the host with the same IEEE additions,
                                               so state order == distance order and every comparison is exact. */
+    uint32_t *dc_edges;           /* [B, MP]   DistributionCenter with an automaton: every CSR row re-ordered by weight code,
+                                              entry = col | code << 16 (derived by ge_prepare bit 4), or NULL: the cutoff search then
+                                              visits only the row prefix that can stay within the cutoff (csrc/ge_dc.cu) */
     double *wmin;                 /* [B]       smallest edge weight of the instance (derived), or NULL: lets the cutoff
                                               SSSP skip nodes that cannot relax anything within the cutoff */
     double *wmat;                 /* [B, N, N] dense float64 weight matrix = the reference's self.adj (derived by
@@ -191,7 +195,8 @@ int ge_build_adjacency(const ge_batch *batch, void *stream);
  *       bit3 labelled alternative heuristics -> heuristic_alt (SteinerTree 1 < n_dests < N-1, TSP, MaxIndependentSet),
  *       bit1 Multicast max_distance from u01[B] (the reference's np.random.rand() draw); u01 == NULL takes the draw
  *            ge_generate left in max_dist32 (a pure function of seed and global env id),
- *       bit2 DistributionCenter in-range tables. */
+ *       bit2 DistributionCenter in-range tables,
+ *       bit4 DistributionCenter weight-sorted edge list dc_edges (needs wcode). */
 int ge_prepare(const ge_batch *batch, int what, const double *u01, void *stream);
 int ge_features(const ge_batch *batch, void *stream);
 int ge_generate(const ge_batch *batch, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32,
@@ -252,7 +257,8 @@ int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_act
 /* PIPELINED end-to-end step with pinned (device-mapped) HOST buffers.  The batch is cut into `chunks` slices; each slice
  * runs copy-in -> step kernel -> write-back on its own branch of ONE CUDA graph, so slice i's results cross PCIe while
  * slice i+1 is stepping and slice i+2's actions arrive.  Results are written back by a small copy kernel straight into
- * the caller's four host arrays (coalesced 128-byte PCIe writes; no staging layout imposed on the host side).  Blocks
+ * the caller's four host arrays (coalesced 128-byte PCIe writes; no staging layout imposed on the host side), and the step
+ * kernels read the actions straight from h_actions (zero-copy; GE_PIPE_ZC=0 copies them to d_actions first).  Blocks
  * until the results are visible to the host (spin on stream completion).  h_solution_cost / h_mask_bits may be NULL. */
 int ge_step_host_pipelined(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                            float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits,

@@ -264,7 +264,7 @@ def test_spatial_tsp_generation_is_euclidean():
 
 
 @pytest.mark.parametrize("cfg", [("ShortestPath-v0", 10, 20, {}), ("LongestPath-v0", 50, 200, {"parenting": 2}),
-                                 ("SteinerTree-v0", 40, 100, {"n_dests": 4}), ("TSP-v0", 100, 400, {"parenting": 1}),
+                                 ("SteinerTree-v0", 40, 100, {"n_dests": 4}), ("TSP-v0", 20, 60, {"parenting": 1}),
                                  ("DistributionCenter-v0", 100, 400, {"parenting": 2}), ("MulticastRouting-v0", 60, 200, {"n_dests": 3, "parenting": 4})],
                          ids=lambda c: c[0][:-3])
 def test_instance_pool_gives_finished_envs_a_fresh_instance(cfg):
