@@ -589,7 +589,7 @@ def run_ours(args):
     flush = L2Flush(torch, D.dev, args.flush)
     sampler = ClockSampler(D.local) if rank == 0 else None
     t_all = time.time()
-    head = measure_workload(D, flush, wl, B, K, W, args, host_side_policy=True, sampler=sampler)
+    head = measure_workload(D, flush, wl, B, K, W, args, host_side_policy=not args.e2e_device_policy, sampler=sampler)
     if world == 1 and not args.no_cpu:
         head["cpu_baseline"] = cpu_rate(wl, args.cpu_seconds)
     head["cpu_reference_python"] = python_reference_entry(wl)
@@ -682,6 +682,8 @@ def main():
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
     ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],
                     help="pipelined: ge_step_host in chunks on two streams (copies overlap kernels); single: one copy-in / kernel / copy-out")
+    ap.add_argument("--e2e-device-policy", action="store_true",
+                    help="headline e2e: draw the actions with the device sampler between calls (untimed) instead of the host numpy policy")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the pipelined end-to-end step")
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")

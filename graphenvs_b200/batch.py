@@ -95,6 +95,8 @@ class BatchedGraphEnv:
         if env_id == "DistributionCenter-v0":
             T["targets"] = z((B, max(d.n_targets, 1)), torch.int32)
             T["in_range"] = z((B, max(d.n_targets, 1), d.NW), torch.int32)
+            if 0 < d.n_targets <= 128 and N <= 1024 and not force_warp and int(P.get("parenting", 2)) == 2:
+                T["in_range_t"] = z((B, N, 4), torch.int32)          # transposed: per node the targets that have it in range
         T["heuristic"] = z((B,), torch.float64)
         self.heuristic_device_name = None
         if self.is_eval_env:
@@ -135,7 +137,7 @@ class BatchedGraphEnv:
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
         for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "dc_edges", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
-                     "max_dist32", "targets", "in_range", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
+                     "max_dist32", "targets", "in_range", "in_range_t", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)

@@ -457,6 +457,7 @@ bool ge_dc_eligible(const ge_batch *d);
 int ge_dc_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_dc_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 int ge_dc_build_edges(const ge_batch *d, cudaStream_t st);
+int ge_dc_build_transposed(const ge_batch *d, cudaStream_t st);
 // eval heuristic kernels (ge_heuristics.cu)
 int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
@@ -588,6 +589,7 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
         if ((rc = set_smem(prep_inrange_kernel, smem))) return rc;
         prep_inrange_kernel<<<(unsigned)((jobs + GE_WPB - 1) / GE_WPB), GE_WPB * 32, smem, st>>>(*d, wpw);
         GE_CUDA_OK(cudaGetLastError());
+        if ((rc = ge_dc_build_transposed(d, st))) return rc;
     }
     return GE_OK;
 }
@@ -848,7 +850,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     if (d->adj_bits) o->adj_bits = d->adj_bits + (adj_tiled(*d) ? (b >> 5) * (size_t)d->N * 32 * d->NW : b * (size_t)d->ADJS);
     ADV(rev, d->MP); ADV(esrc, d->MP); ADV(wsort, d->MP); ADV(wcode, d->MP); ADV(dc_edges, d->MP); ADV(wmin, 1); ADV(wmat, (size_t)d->N * d->N);
     ADV(src, 1); ADV(dest, 1); ADV(target_bits, d->NW); ADV(node_cost, d->N); ADV(node_xy, 2 * d->N); ADV(max_dist32, 1);
-    ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(heuristic, 1); ADV(heuristic_alt, 1); ADV(features, 5 * d->N);
+    ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(in_range_t, 4 * (size_t)d->N); ADV(heuristic, 1); ADV(heuristic_alt, 1); ADV(features, 5 * d->N);
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
     ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
     ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);

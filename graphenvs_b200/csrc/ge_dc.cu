@@ -153,6 +153,42 @@ __device__ __forceinline__ uint32_t dc_union_in_range(const ge_batch &d, int b, 
     return (lane < NW) ? acc : 0u;
 }
 
+// The same union from the TRANSPOSED table (ge_batch.in_range_t: per node v a 128-bit set of the targets that have v in
+// range): mask[v] = (tin[v] & uncovered targets) != 0.  One coalesced 16-byte load per node, no compaction of the target
+// list, no dependent row loads: 16 independent loads per lane at N=500 instead of ~50 rows of 64 bytes fetched through a
+// list (the OR of rows was 16.5 % of the instructions and 15 % of the stall samples of the step,
+// profiles/r02_dc_step_kernel_v2.md).  More bytes (8 KB instead of ~3 KB per step), fewer instructions and no chain.
+__device__ __forceinline__ uint32_t dc_union_transposed(const ge_batch &d, int b, int lane, uint32_t covw) {
+    const int N = d.N, NW = d.NW, NT = d.n_targets;
+    const int32_t *tg = d.targets + (size_t)b * NT;
+    uint32_t U[4] = {0u, 0u, 0u, 0u};                                 // uncovered targets, bit t = target t (warp-uniform)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int t = 32 * k + lane;
+        int node = 0;
+        if (t < NT) node = tg[t];
+        const uint32_t cw = __shfl_sync(GE_FULL, covw, (node >> 5) & 31);
+        U[k] = __ballot_sync(GE_FULL, t < NT && !((cw >> (node & 31)) & 1u));
+    }
+    const uint4 *tin = reinterpret_cast<const uint4 *>(d.in_range_t) + (size_t)b * N;
+    uint32_t mine = 0;
+    for (int j0 = 0; j0 < NW; j0 += 4) {
+        uint4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = ((j0 + k) << 5) + lane;
+            x[k] = (j0 + k < NW && v < N) ? __ldg(tin + v) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t hit = (x[k].x & U[0]) | (x[k].y & U[1]) | (x[k].z & U[2]) | (x[k].w & U[3]);
+            const uint32_t wd = __ballot_sync(GE_FULL, hit != 0u);
+            if (lane == j0 + k) mine = wd;
+        }
+    }
+    return mine;
+}
+
 __device__ __forceinline__ void dc_store_mask(const ge_batch &d, int b, int lane, uint32_t m) {
     if (lane >= d.AW) return;
     d.mask_bits[(size_t)b * d.AW + lane] = m;
@@ -173,7 +209,7 @@ __device__ __forceinline__ void dc_store_mask(const ge_batch &d, int b, int lane
 // mask right after reset(): nothing taken, nothing covered
 __device__ __forceinline__ uint32_t dc_reset_mask(const ge_batch &d, int b, int lane, uint32_t tail, uint16_t *live) {
     if (d.parenting != 2) return tail;
-    return dc_union_in_range(d, b, lane, 0u, live) & tail;
+    return ((d.in_range_t && d.n_targets <= 128) ? dc_union_transposed(d, b, lane, 0u) : dc_union_in_range(d, b, lane, 0u, live)) & tail;
 }
 
 template <bool SAMPLED>
@@ -249,7 +285,9 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
         rew += (float)gained;
         reward = (double)rew;
         __syncwarp();
-        if (d.parenting == 2) maskw = dc_union_in_range(d, b, lane, covw, s.cur) & ~takenw & tail;   // the lists are free again
+        if (d.parenting == 2)
+            maskw = ((d.in_range_t && d.n_targets <= 128) ? dc_union_transposed(d, b, lane, covw)
+                                                           : dc_union_in_range(d, b, lane, covw, s.cur /* free again */)) & ~takenw & tail;
         else maskw = ~takenw & tail;
         if (!__any_sync(GE_FULL, (tgtw & ~covw) != 0u)) { done = 1; solved = 1; sol = cost; }
     }
@@ -332,7 +370,36 @@ __global__ void __launch_bounds__(256) dc_edges_kernel(ge_batch d) {
             if (wc[e] == c) out[pos++] = (uint32_t)col[e] | ((uint32_t)c << 16);
 }
 
+// in_range_t[v] bit t = in_range[t] bit v (128 targets per node).  One warp per env.
+__global__ void __launch_bounds__(256) dc_transpose_kernel(ge_batch d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= d.B) return;
+    const int N = d.N, NW = d.NW, NT = d.n_targets;
+    uint32_t *tin = d.in_range_t + (size_t)b * N * 4;
+    for (int i = lane; i < 4 * N; i += 32) tin[i] = 0;
+    __syncwarp();
+    __threadfence_block();
+    const uint32_t *ir = d.in_range + (size_t)b * NT * NW;
+    for (int t = 0; t < NT; ++t)
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t bits = ir[(size_t)t * NW + w];
+            while (bits) {
+                const int v = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (v < N) atomicOr(&tin[4 * v + (t >> 5)], 1u << (t & 31));
+            }
+        }
+}
+
 }  // namespace
+
+int ge_dc_build_transposed(const ge_batch *d, cudaStream_t st) {
+    if (!d->in_range_t || !d->in_range || d->n_targets > 128) return GE_OK;
+    dc_transpose_kernel<<<(d->B + 7) / 8, 256, 0, st>>>(*d);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "dc_transpose_kernel launch: %s", cudaGetErrorString(e));
+}
 
 int ge_dc_build_edges(const ge_batch *d, cudaStream_t st) {
     if (!d->dc_edges || !d->wcode) return GE_OK;

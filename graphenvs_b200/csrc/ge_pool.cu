@@ -106,7 +106,7 @@ extern "C" int ge_pool_refill(const ge_batch *live, const ge_batch *banks, int n
     POOL_ADD(rev, d.MP * 4); POOL_ADD(esrc, d.MP * 4); POOL_ADD(wsort, d.MP * 8); POOL_ADD(wcode, d.MP); POOL_ADD(dc_edges, d.MP * 4); POOL_ADD(wmin, 8);
     POOL_ADD(wmat, (size_t)d.N * d.N * 8); POOL_ADD(src, 4); POOL_ADD(dest, 4); POOL_ADD(target_bits, d.NW * 4);
     POOL_ADD(node_cost, d.N * 4); POOL_ADD(node_xy, d.N * 8); POOL_ADD(max_dist32, 4); POOL_ADD(targets, d.n_targets * 4);
-    POOL_ADD(in_range, (size_t)d.n_targets * d.NW * 4); POOL_ADD(heuristic, 8); POOL_ADD(heuristic_alt, 8);
+    POOL_ADD(in_range, (size_t)d.n_targets * d.NW * 4); POOL_ADD(in_range_t, (size_t)d.N * 16); POOL_ADD(heuristic, 8); POOL_ADD(heuristic_alt, 8);
     POOL_ADD(features, d.N * 20); POOL_ADD(mask0_bits, d.AW * 4);
 #undef POOL_ADD
     if (rc) return rc;

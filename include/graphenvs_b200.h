@@ -133,6 +133,8 @@ typedef struct ge_batch {
     float *max_dist32;            /* [B]      Multicast MAX_DISTANCE column value */
     int32_t *targets;             /* [B, n_targets] DistributionCenter target node ids */
     uint32_t *in_range;           /* [B, n_targets, NW] nodes within max_distance of each target */
+    uint32_t *in_range_t;         /* [B, N, 4] the same table transposed: per node a 128-bit set of the targets that have it in
+                                              range (n_targets <= 128; derived by ge_prepare bit 2 when non-NULL), or NULL */
     double *heuristic;            /* [B]      info['heuristic_solution'] */
     double *heuristic_alt;        /* [B]      info['heuristic_device']: labelled alternative where the reference's value is defined by
                                               networkx iteration order (Steiner shortest-path heuristic, TSP nearest neighbour, greedy
