@@ -420,6 +420,20 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         assert int(h_flg.numpy()[:, 2].max()) == 0, "policy produced an invalid action"
     e2e_s_max = D.reduce([e2e_s], "max")[0]
     e2e_val = envs_all * Ke / e2e_s_max
+    e2e_dev_val = None
+    if host_side_policy:       # the same call with the actions drawn by the device sampler between calls (untimed): the GPU
+        t_dev = 0.0            # does not idle for the milliseconds the numpy policy takes, which by itself costs ~10 us per call
+        for k in range(3 + Ke):
+            env.sample_actions(SEED, 7)
+            h_act.copy_(env.actions_dev)
+            flush()
+            torch.cuda.synchronize()
+            c0 = time.perf_counter()
+            stepper()
+            c1 = time.perf_counter()
+            if k >= 3:
+                t_dev += c1 - c0
+        e2e_dev_val = envs_all * Ke / D.reduce([t_dev], "max")[0]
     h2d = B * 4
     d2h = B * 16 + B * d.AW * 4
 
@@ -474,6 +488,7 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "gpu_launches": (1 if fused else 2) * K,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
+                "value_with_device_policy_between_calls": e2e_dev_val,
                 "timed": ("sum of ge_step_host calls: pinned H2D actions, step kernel, D2H of reward/flags/solution_cost/packed mask, "
                           "completion wait (%s%s); policy between calls untimed" % (args.e2e, ", %d slices" % args.e2e_chunks if args.e2e == "pipelined" else ""))},
         "e2e_obs": e2e_obs,

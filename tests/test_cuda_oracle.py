@@ -321,3 +321,21 @@ def test_obs_nodes_is_the_x_tensor_of_obs_graph():
         assert torch.equal(env.obs_nodes(7, 11), x[7:18])
         name = env.step_kernel_name(sampled=True)
         assert name.endswith(">") and "step_kernel<" in name
+
+
+def test_distribution_center_transposed_mask_equals_row_union():
+    """The optional transposed in-range table (per node a 128-bit target set, csrc/ge_dc.cu:dc_union_transposed) builds
+    the same masks and trajectories as the OR of the uncovered targets' rows."""
+    B, T = 400, 40
+    envs = []
+    for tr in (False, True):
+        e = BatchedGraphEnv("DistributionCenter-v0", B, 120, 500, parenting=2, auto_reset=True, dc_transposed=tr)
+        e.generate(seed=12)
+        e.reset()
+        assert ("in_range_t" in e.t) == tr
+        for t in range(T):
+            e.step_sampled(6, t)
+        torch.cuda.synchronize()
+        envs.append(e)
+    for name in ("traj", "acc", "mask_bits", "node_bits", "node_bits2", "cost"):
+        assert torch.equal(envs[0].t[name], envs[1].t[name]), name
