@@ -45,6 +45,9 @@ WORKLOADS = {
                         75000, "DistributionCenter-v0 n_nodes=500 n_edges=4000 parenting=2, 131072 envs/GPU"),
     "densest": ("DensestSubgraph-v0", 500, 4000, dict(parenting=1), 65536, 2000,
                 "DensestSubgraph-v0 n_nodes=500 n_edges=4000 parenting=1, 65536 envs/GPU"),
+    # the reference's ninth id (not one of BASELINE's configs): row(head) + one edge weight per step
+    "perishable": ("PerishableProductDelivery-v0", 50, 200, dict(n_products=3, parenting=1), 65536, 150,
+                   "PerishableProductDelivery-v0 n_nodes=50 n_edges=200 n_products=3 parenting=1, 65536 envs/GPU"),
 }
 DEFAULT_WORKLOAD = "cfg2_longest_path"
 METRIC, UNIT = "env-steps/sec", "env-steps/s"
@@ -100,6 +103,9 @@ def layout_bytes_per_step(env):
         graph = rows * (8 + deg * 12) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
     elif k == "DensestSubgraph-v0":
         graph = nw4 + 16 + 2 * nw4
+    elif k == "PerishableProductDelivery-v0":
+        graph = nw4 + 8 + deg * 12 + 8 * d.n_dests + 4       # row(head) bits, the head's CSR row scanned for the edge, pickups / dropoffs
+        state = 2 * (4 + 16)                                  # head, counters
     else:  # MaxIndependentSet (lane family)
         graph = 4
     return float(fixed + mask + state + graph)

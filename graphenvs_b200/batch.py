@@ -39,9 +39,9 @@ class BatchedGraphEnv:
         d = _native.GeBatch()
         d.kind, d.B, d.N, d.M = self.spec.kind, self.B, self.N, self.M
         d.parenting = int(P.get("parenting", -1))
-        d.n_dests = int(P.get("n_dests", 0))
+        d.n_dests = int(P.get("n_dests", P.get("n_products", 0)))     # PerishableProductDelivery: products
         d.n_choices = int(P.get("n_choices", 0))
-        d.n_targets = int(P.get("target_count", 0))
+        d.n_targets = int(P.get("target_count", 0)) if env_id != "PerishableProductDelivery-v0" else 2 * int(P["n_products"])
         d.flags = ((1 if auto_reset else 0) | (2 if env_id == "TSP-v0" else 0) | (0 if P.get("weighted", True) else 4)
                    | (8 if force_warp else 0))
         d.env_id0 = int(env_id0)
@@ -66,7 +66,9 @@ class BatchedGraphEnv:
             B32 = (B + 31) // 32 * 32                             # whole tiles of 32 envs for the N <= 64 layout
             self._adj_store = z((B32 * d.ADJS,), torch.int32)
             T["adj_bits"] = self._adj_store
-            if N <= 64 and self.spec.step_w == "f64":
+            if env_id == "PerishableProductDelivery-v0":
+                pass                                                  # looks its one edge weight up in the CSR row
+            elif N <= 64 and self.spec.step_w == "f64":
                 T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
             elif self.spec.step_w == "f64":
                 T["wsort"] = z((B, d.MP), torch.float64)             # destination-sorted weights: O(1) adj[u, v] by bit rank
@@ -92,6 +94,9 @@ class BatchedGraphEnv:
             T["max_dist32"] = z((B,), torch.float32)
             T["edge_bits"] = z((B, d.MW), torch.int32)
             T["dist32"] = z((B, N), torch.float32)
+        if env_id == "PerishableProductDelivery-v0":
+            T["max_dist32"] = z((B,), torch.float32)                 # delivery time (the TIME_LEFT columns)
+            T["targets"] = z((B, d.n_targets), torch.int32)           # pickups, then dropoffs
         if env_id == "DistributionCenter-v0":
             T["targets"] = z((B, max(d.n_targets, 1)), torch.int32)
             T["in_range"] = z((B, max(d.n_targets, 1), d.NW), torch.int32)
@@ -199,6 +204,10 @@ class BatchedGraphEnv:
                     tl = np.asarray(ins.dests, dtype=np.int32).ravel()
                     assert tl.shape[0] == d.n_targets
                     targets[b, :d.n_targets] = tl
+            if self.env_id == "PerishableProductDelivery-v0":
+                tl = np.asarray(ins.dests, dtype=np.int32).ravel()
+                assert tl.shape[0] == d.n_targets
+                targets[b, :d.n_targets] = tl
             if ins.node_cost is not None:
                 ncost[b] = np.asarray(ins.node_cost, dtype=np.float64).astype(np.float32)
             if ins.node_xy is not None:
@@ -340,7 +349,7 @@ class BatchedGraphEnv:
             links = np.stack([np.repeat(np.arange(N, dtype=np.int32), deg), col[i, :M]], axis=1).astype(np.int32)
             ins = Instance(n_nodes=N, links=links, w64=w[i, :M].astype(np.float64), src=int(src[i]), dest=int(dest[i]),
                            heuristic=float(heur[i]))
-            if self.env_id == "DistributionCenter-v0":
+            if self.env_id in ("DistributionCenter-v0", "PerishableProductDelivery-v0"):
                 ins.dests = tg[i, :d.n_targets].astype(np.int32)
             elif tb is not None:
                 bits = np.unpackbits(tb[i].view(np.uint8), bitorder="little")[:N]

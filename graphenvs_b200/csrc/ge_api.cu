@@ -37,7 +37,8 @@ extern "C" int ge_set_error(int code, const char *fmt, ...) {
 
 __host__ __device__ static inline bool is_edge_kind(int kind) { return kind == GE_STEINER_TREE || kind == GE_MULTICAST_ROUTING; }
 static bool uses_adj(int kind) {
-    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_DENSEST_SUBGRAPH;
+    return kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH || kind == GE_TSP || kind == GE_DENSEST_SUBGRAPH ||
+           kind == GE_PERISHABLE_DELIVERY;
 }
 
 // ------------------------------------------------------------------ kernels
@@ -234,6 +235,15 @@ __device__ __forceinline__ float node_value(const ge_batch &d, int b, int v, int
         if (c == 2) return (float)((tgt[v >> 5] >> (v & 31)) & 1u);
         if (c == 3) return (float)((aux[v >> 5] >> (v & 31)) & 1u);
         return (float)d.max_distance;
+    case GE_PERISHABLE_DELIVERY: {   // perishable_product_delivery.py:38-41: IS_HEAD | HAS_P[5] | NEEDS_P[5] | TIME_LEFT[5]
+        if (c == 0) return (float)(v == d.head[b]);
+        const int i = (c - 1) % 5, grp = (c - 1) / 5, P = d.n_dests;
+        if (i >= P) return 0.f;
+        const int st = (d.counters[(size_t)b * 4] >> (2 * i)) & 3;
+        const int32_t *tg = d.targets + (size_t)b * d.n_targets;
+        if (grp == 0) return st == 0 ? (float)(v == tg[i]) : (st == 1 ? -1.f : 0.f);
+        if (grp == 1) return st == 2 ? 0.f : (float)(v == tg[P + i]);
+        return st == 2 ? 0.f : maxd; }
     }
     return 0.f;
 }
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     case GE_TSP: case GE_MULTICAST_ROUTING: dyn = 4; break;
     case GE_DENSEST_SUBGRAPH: dyn = 1; break;
     case GE_DISTRIBUTION_CENTER: dyn = 5; break;
+    case GE_PERISHABLE_DELIVERY: dyn = 16; break;
     default: dyn = 2;
     }
     const int F = dyn + 5, Fe = is_edge_kind(kind) ? 2 : 1;
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     const uint32_t *tgt = d.target_bits ? d.target_bits + (size_t)b * d.NW : nullptr;
     const bool seeded = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH;
     const int src = seeded ? d.src[b] : 0, dest = seeded ? d.dest[b] : 0;
-    const float maxd = kind == GE_MULTICAST_ROUTING ? d.max_dist32[b] : 0.f;
+    const float maxd = (kind == GE_MULTICAST_ROUTING || kind == GE_PERISHABLE_DELIVERY) ? d.max_dist32[b] : 0.f;
     {   // node section: element i = (v, c) with v = i / F; the pair advances by (blockDim / F, blockDim % F) per trip
         int v = (int)threadIdx.x / F, c = (int)threadIdx.x - v * F;
         const int dv = (int)blockDim.x / F, dc = (int)blockDim.x - dv * F;
@@ -348,6 +359,32 @@ __global__ void __launch_bounds__(GE_WPB * 32) prep_sssp_kernel(ge_batch d, int 
             }
         }
     }
+}
+
+// PerishableProductDelivery eval heuristic (perishable_product_delivery.py:147-153): for every product, Dijkstra distance
+// head(0) -> pickup plus pickup -> dropoff (curr_node is never advanced in the reference), summed in product order.
+__global__ void __launch_bounds__(GE_WPB * 32) prep_ppd_kernel(ge_batch d, int words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    const int P = d.n_dests;
+    const int32_t *tg = d.targets + (size_t)b * d.n_targets;
+    double from_head[5];
+    sssp_warp(d, b, lane, s, 0, 0.0, false);
+    __syncwarp();
+    for (int i = 0; i < P; ++i) from_head[i] = __longlong_as_double((long long)s.q[tg[i]]);
+    __syncwarp();
+    double total = 0.0;
+    for (int i = 0; i < P; ++i) {
+        sssp_warp(d, b, lane, s, tg[i], 0.0, false);
+        __syncwarp();
+        total += from_head[i];
+        total += __longlong_as_double((long long)s.q[tg[P + i]]);
+        __syncwarp();
+    }
+    if (lane == 0) d.heuristic[b] = total;
 }
 
 // MST total weight (steiner_tree.py:81): Prim in fp64; the multiset of MST weights is
@@ -458,13 +495,16 @@ int ge_dc_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool
 int ge_dc_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 int ge_dc_build_edges(const ge_batch *d, cudaStream_t st);
 int ge_dc_build_transposed(const ge_batch *d, cudaStream_t st);
+// PerishableProductDelivery (ge_ppd.cu)
+int ge_ppd_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
+int ge_ppd_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
 // eval heuristic kernels (ge_heuristics.cu)
 int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
 static int check_batch(const ge_batch *d) {
     if (!d) return fail(GE_ERR_ARG, "null batch");
-    if (d->kind < 0 || d->kind > 7) return fail(GE_ERR_ARG, "unknown kind %d", d->kind);
+    if (d->kind < 0 || d->kind > 8) return fail(GE_ERR_ARG, "unknown kind %d", d->kind);
     if (d->B <= 0 || d->N < 2 || d->M < 0) return fail(GE_ERR_ARG, "bad shape B=%d N=%d M=%d", d->B, d->N, d->M);
     if (d->N > 4096) return fail(GE_ERR_UNSUPPORTED, "N=%d > 4096 not supported", d->N);
     if (d->NW != (d->N + 31) / 32 || d->MW != (d->M + 31) / 32) return fail(GE_ERR_ARG, "layout not filled (call ge_fill_layout)");
@@ -560,6 +600,10 @@ int ge_prepare(const ge_batch *d, int what, const double *u01, void *stream) {
             if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
             if ((rc = set_smem(prep_mst_kernel, smem))) return rc;
             prep_mst_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, wpw);
+        } else if (d->kind == GE_PERISHABLE_DELIVERY) {
+            if ((rc = launch_cfg(d, d->B, &blocks, &wpw, &smem))) return rc;
+            if ((rc = set_smem(prep_ppd_kernel, smem))) return rc;
+            prep_ppd_kernel<<<blocks, GE_WPB * 32, smem, st>>>(*d, wpw);
         } else if (d->kind == GE_MULTICAST_ROUTING) {
             if ((rc = ge_heuristics_launch(d, 1, st))) return rc;
         } else if (d->kind == GE_STEINER_TREE || d->kind == GE_TSP) {
@@ -599,6 +643,7 @@ int ge_reset(const ge_batch *d, const uint8_t *select, void *stream) {
     int rc = check_batch(d);
     if (rc) return rc;
     if (uses_adj(d->kind) && !d->adj_bits) return fail(GE_ERR_ARG, "kind %d needs adj_bits (ge_build_adjacency)", d->kind);
+    if (d->kind == GE_PERISHABLE_DELIVERY) return ge_ppd_reset(d, select, (cudaStream_t)stream);
     if (ge_lane_eligible(d)) return ge_lane_reset(d, select, (cudaStream_t)stream);
     if (ge_group_eligible(d)) return ge_group_reset(d, select, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_reset(d, select, (cudaStream_t)stream);
@@ -617,6 +662,7 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     int rc = check_batch(d);
     if (rc) return rc;
     if (!actions || !out || !out->reward || !out->flags || !out->solution_cost) return fail(GE_ERR_ARG, "null step buffers");
+    if (d->kind == GE_PERISHABLE_DELIVERY) return ge_ppd_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_lane_eligible(d)) return ge_lane_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_group_eligible(d)) return ge_group_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
     if (ge_incr_eligible(d)) return ge_incr_step(d, actions, out, sampled, seed, t, (cudaStream_t)stream);
@@ -656,7 +702,8 @@ int ge_sample_actions(const ge_batch *d, uint64_t seed, uint32_t t, int32_t *act
 }
 
 int ge_obs_len(const ge_batch *d) {
-    int dyn = (d->kind == GE_TSP || d->kind == GE_MULTICAST_ROUTING) ? 4 : d->kind == GE_DENSEST_SUBGRAPH ? 1 : d->kind == GE_DISTRIBUTION_CENTER ? 5 : 2;
+    int dyn = (d->kind == GE_TSP || d->kind == GE_MULTICAST_ROUTING) ? 4 : d->kind == GE_DENSEST_SUBGRAPH ? 1 : d->kind == GE_DISTRIBUTION_CENTER ? 5
+              : d->kind == GE_PERISHABLE_DELIVERY ? 16 : 2;
     int Fe = is_edge_kind(d->kind) ? 2 : 1;
     return d->N * (dyn + 5) + d->M * Fe + 2 * d->M;
 }
@@ -693,7 +740,7 @@ int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *strea
     return GE_OK;
 }
 
-int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }
+int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }   // (a sampler / obs call never mirrors)
 
 int ge_mask_bytes_current(const ge_batch *d) { return d && d->mask_bytes && !ge_incr_eligible(d); }
 
@@ -716,7 +763,8 @@ const char *ge_step_kernel_name(const ge_batch *d, int sampled) {
     if (!d) return "";
     const char *fam;
     char shape[48] = "";
-    if (ge_lane_eligible(d)) { fam = "lane_step_kernel"; snprintf(shape, sizeof(shape), "STAGED=%d,SAMPLED=%d", (d->kind == GE_LONGEST_PATH || d->kind == GE_TSP) && d->parenting >= 2, sampled); }
+    if (d->kind == GE_PERISHABLE_DELIVERY) { fam = "ppd_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }
+    else if (ge_lane_eligible(d)) { fam = "lane_step_kernel"; snprintf(shape, sizeof(shape), "STAGED=%d,SAMPLED=%d", (d->kind == GE_LONGEST_PATH || d->kind == GE_TSP) && d->parenting >= 2, sampled); }
     else if (ge_group_eligible(d)) { fam = "group_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,G=%d", sampled, d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32); }
     else if (ge_incr_eligible(d)) {
         if (d->kind == GE_MAX_INDEPENDENT_SET) { fam = "incr_mis_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }

@@ -308,6 +308,77 @@ __global__ void generate_kernel(ge_batch d, uint64_t seed, int32_t *__restrict__
 
 __global__ void clear_fallbacks_kernel() { g_generate_fallbacks = 0; }
 
+// PerishableProductDelivery terminals (perishable_product_delivery.py:96-114), distribution parity: delivery time
+// U(dt_mn, dt_mx) with the constructor's range (:51-58); per product a pickup uniform among the unused nodes and a dropoff
+// uniform among the unused nodes within the delivery time of it (Dijkstra distances; the reference reads them from
+// Floyd-Warshall).  Where the reference would redraw the whole graph (no dropoff in range) this kernel redraws the pickup,
+// and after 32 tries takes the nearest unused node (counted in ge_generate_fallbacks).  Runs after the CSR exists.
+__global__ void __launch_bounds__(GE_WPB * 32) ppd_terminals_kernel(ge_batch d, uint64_t seed, int words_per_warp, int weighted) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * GE_WPB + warp;
+    if (b >= d.B) return;
+    Scr s = carve(smem + (size_t)warp * words_per_warp, d);
+    const int N = d.N, NW = d.NW, P = d.n_dests;
+    const uint64_t gid = (uint64_t)(uint32_t)(d.env_id0 + b), tseed = seed ^ 0x9FB21C651E98DF25ull;
+    const double avg_degree = (double)d.M / (double)N;
+    double avg_dist = log((double)N) / log(avg_degree);
+    if (weighted) avg_dist = avg_dist * (0.3 + 1.0) / 2.0;
+    const double dt_mn = avg_dist * 0.6, dt_mx = avg_dist * 1.4;
+    const double u = (double)(mix64(tseed, gid, 1) >> 11) * (1.0 / 9007199254740992.0);
+    const double dt = u * (dt_mx - dt_mn) + dt_mn;
+    if (lane == 0) d.max_dist32[b] = (float)dt;
+    int32_t *tg = d.targets + (size_t)b * d.n_targets;
+    for (int w = lane; w < NW; w += 32) s.aux[w] = 0;                       // used nodes
+    __syncwarp();
+    uint64_t ctr = 16;
+    for (int i = 0; i < P; ++i) {
+        int pickup = -1, dropoff = -1;
+        for (int attempt = 0; attempt < 33 && dropoff < 0; ++attempt) {
+            do { pickup = (int)bounded((uint32_t)(mix64(tseed, gid, ctr++) >> 32), (uint32_t)N); } while (tbit(s.aux, pickup));
+            sssp_warp(d, b, lane, s, pickup, 0.0, false);
+            __syncwarp();
+            const bool last = attempt == 32;
+            // candidates: unused nodes other than the pickup within the delivery time (last try: the nearest unused node)
+            int cnt = 0;
+            for (int v0 = 0; v0 < N; v0 += 32) {
+                const int v = v0 + lane;
+                const bool c = v < N && v != pickup && !tbit(s.aux, v) && __longlong_as_double((long long)s.q[v]) < dt + 1e-6;
+                cnt += __popc(__ballot_sync(GE_FULL, c));
+            }
+            if (cnt > 0) {
+                int r = (int)bounded((uint32_t)(mix64(tseed, gid, ctr++) >> 32), (uint32_t)cnt);
+                for (int v0 = 0; v0 < N && dropoff < 0; v0 += 32) {
+                    const int v = v0 + lane;
+                    const bool c = v < N && v != pickup && !tbit(s.aux, v) && __longlong_as_double((long long)s.q[v]) < dt + 1e-6;
+                    const unsigned bal = __ballot_sync(GE_FULL, c);
+                    const int k = __popc(bal);
+                    if (r < k) dropoff = v0 + nth_set_bit(bal, r); else r -= k;
+                }
+            } else if (last) {
+                double bd = __longlong_as_double(0x7ff0000000000000ll);
+                int bv = -1;
+                for (int v = lane; v < N; v += 32)
+                    if (v != pickup && !tbit(s.aux, v)) { const double dv = __longlong_as_double((long long)s.q[v]); if (dv < bd) { bd = dv; bv = v; } }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(GE_FULL, bd, o);
+                    const int ov = __shfl_xor_sync(GE_FULL, bv, o);
+                    if (ov >= 0 && (bv < 0 || od < bd || (od == bd && ov < bv))) { bd = od; bv = ov; }
+                }
+                dropoff = bv;
+                if (lane == 0) atomicAdd(&g_generate_fallbacks, 1u);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            tg[i] = pickup; tg[P + i] = dropoff;
+            s.aux[pickup >> 5] |= 1u << (pickup & 31);
+            if (dropoff >= 0) s.aux[dropoff >> 5] |= 1u << (dropoff & 31);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 extern "C" int ge_generate(const ge_batch *d, uint64_t seed, int32_t *row_ptr, int32_t *col, double *w64, float *w32, void *stream) {
@@ -331,7 +402,20 @@ extern "C" int ge_generate(const ge_batch *d, uint64_t seed, int32_t *row_ptr, i
     clear_fallbacks_kernel<<<1, 1, 0, (cudaStream_t)stream>>>();
     generate_kernel<<<(d->B + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(*d, seed, row_ptr, col, w64, w32, wpw, wpb, weighted);
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "generate_kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "generate_kernel launch: %s", cudaGetErrorString(e));
+    if (d->kind == GE_PERISHABLE_DELIVERY) {
+        if (!w64 || !d->targets || !d->max_dist32 || d->n_targets != 2 * d->n_dests || 2 * d->n_dests > d->N)
+            return ge_set_error(GE_ERR_ARG, "ge_generate: PerishableProductDelivery needs w64, targets[2 * n_products], max_dist32 and 2 * n_products <= n_nodes");
+        ge_batch dd = *d;                                   // the terminals kernel reads the CSR just written
+        dd.row_ptr = row_ptr; dd.col = col; dd.w64 = w64;
+        const int sw = scratch_words(dd);
+        const size_t sm = (size_t)sw * GE_WPB * sizeof(uint32_t);
+        if ((rc = ge_grant_smem((const void *)ppd_terminals_kernel, sm))) return rc;
+        ppd_terminals_kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, sm, (cudaStream_t)stream>>>(dd, seed, sw, weighted);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return ge_set_error(GE_ERR_CUDA, "ppd_terminals_kernel launch: %s", cudaGetErrorString(e));
+    }
+    return GE_OK;
 }
 
 // Number of envs of the most recent ge_generate on `stream` whose rejection loop ran out of attempts and that were

@@ -92,9 +92,62 @@ def _undirected_edges(adj):
         seen.add(u)
 
 
+def _perishable_instance(p):
+    """PerishableProductDelivery reset() (perishable_product_delivery.py:72-117), draw for draw: the numpy draws (weight
+    matrix, delivery time, pickups / dropoffs) happen INSIDE the retry loop, the pickup / dropoff lists are NOT cleared
+    between attempts (:78-79 sit before the loop), and a dropoff is drawn from the keys of nx.floyd_warshall's dict of the
+    pickup in ITS insertion order: the node itself, the far ends of its incident edges in G.edges order, then the
+    remaining nodes ascending (nx:algorithms/shortest_paths/dense.py).  Distances are the literal Floyd-Warshall values."""
+    N, E, P = p["n_nodes"], p["n_edges"], p["n_products"]
+    weighted = p.get("weighted", True)
+    rnd = np.random
+    pickups, dropoffs = [-1] * P, [-1] * P
+    while True:
+        edge_order = []
+        adj = gnm_adjacency(N, E, edge_order)
+        if not _connected(adj, N):
+            continue
+        delay = (rnd.randint(3, 10, size=(N, N)) if weighted else rnd.randint(10, 11, size=(N, N))) / 10.0
+        und = list(_undirected_edges(adj))                          # G.edges order, u < v
+        delivery_time = rnd.rand() * (p["dt_mx"] - p["dt_mn"]) + p["dt_mn"]
+        dist = np.full((N, N), np.inf)
+        np.fill_diagonal(dist, 0.0)
+        order = [[u] for u in range(N)]                            # key order of dist[u]
+        for u, v in und:
+            w = delay[u, v]
+            dist[u, v] = min(w, dist[u, v]); dist[v, u] = min(w, dist[v, u])
+            order[u].append(v); order[v].append(u)
+        for k in range(N):                                          # for w in G: d = dist[u][w] + dist[w][v]
+            d = dist[:, k:k + 1] + dist[k:k + 1, :]
+            np.minimum(dist, d, out=dist)
+        for u in range(N):
+            have = set(order[u])
+            order[u] += [v for v in range(N) if v not in have]
+        ok = True
+        for i in range(P):
+            pickups[i] = rnd.choice([node for node in range(N) if (node not in pickups) and (node not in dropoffs)])
+            close = [node for node in order[pickups[i]] if dist[pickups[i], node] < delivery_time + 1e-6
+                     and (node not in pickups) and (node not in dropoffs)]
+            if len(close) == 0:
+                ok = False
+                break
+            dropoffs[i] = rnd.choice(close)
+        if ok and (-1 not in pickups) and (-1 not in dropoffs):
+            break
+    links = np.array([(u, v) for u in range(N) for v in adj[u]], dtype=np.int32).reshape(-1, 2)
+    lo = np.minimum(links[:, 0], links[:, 1])
+    hi = np.maximum(links[:, 0], links[:, 1])
+    ins = Instance(n_nodes=N, links=links, w64=delay[lo, hi].astype(np.float64), edge_order=edge_order)
+    ins.dests = np.array([int(x) for x in pickups] + [int(x) for x in dropoffs], dtype=np.int32)   # pickups, then dropoffs
+    ins.max_distance = float(delivery_time)
+    return ins
+
+
 def generate_instance(env_id, p):
     """Instance of `env_id` with constructor parameters `p` (spec.check_ctor_args), consuming the
     global `random` / `numpy.random` streams exactly like the reference's reset()."""
+    if env_id == "PerishableProductDelivery-v0":
+        return _perishable_instance(p)
     N, E = p["n_nodes"], p["n_edges"]
     weighted = p.get("weighted", True)
     n_graph = N - 1 if env_id == "DensestSubgraph-v0" else N       # densest_subgraph.py:59-65

@@ -48,7 +48,7 @@ class _Box:
         self.low, self.high, self.shape = low, high, tuple(shape)
 
 
-_EVERY_STEP_HEURISTIC = ("LongestPath-v0", "DensestSubgraph-v0", "MulticastRouting-v0")
+_EVERY_STEP_HEURISTIC = ("LongestPath-v0", "DensestSubgraph-v0", "MulticastRouting-v0", "PerishableProductDelivery-v0")
 
 
 class GraphEnv(_Base):
@@ -114,9 +114,14 @@ class GraphEnv(_Base):
         c.reset()
         self.src, self.dest, self.dests = ins.src, ins.dest, ins.dests
         self.start = 0
-        self._track = [] if self.env_id == "LongestPath-v0" else set()
+        self._track = [] if self.env_id in ("LongestPath-v0", "PerishableProductDelivery-v0") else set()
         self._head = ins.src
         info = {"mask": self._mask()}
+        if self.env_id == "PerishableProductDelivery-v0":          # perishable_product_delivery.py:158-160
+            P = self.params["n_products"]
+            self.pickups, self.dropoffs = [int(x) for x in ins.dests[:P]], [int(x) for x in ins.dests[P:]]
+            info["pickups"], info["dropoffs"], info["time_left"] = self.pickups, self.dropoffs, ins.max_distance
+            self._head = 0
         obs = self._obs()
         if self.return_graph_obs:
             info["graph_obs"] = graph_from_obs(obs, self.env_id, c.N, c.E)
@@ -151,6 +156,11 @@ class GraphEnv(_Base):
             self._track.append((self._head, a))
             info["edges_taken"] = self._track
             if has_mask:
+                self._head = a
+        elif self.env_id == "PerishableProductDelivery-v0":        # perishable_product_delivery.py:212,220,226
+            info["edges_taken"] = self._track
+            if has_mask or done_b:
+                self._track.append((self._head, a))
                 self._head = a
         elif self.env_id == "DensestSubgraph-v0":                  # densest_subgraph.py:151,193
             if a != c.N - 1:

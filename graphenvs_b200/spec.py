@@ -21,7 +21,7 @@ class EnvSpec:
         """Eval heuristics the GPU computes with the REFERENCE'S value: the tie-independent ones (Dijkstra
         for ShortestPath / LongestPath / SteinerTree n_dests=1, MST weight for n_dests=N-1) and Multicast's union of
         first-found shortest paths (networkx's pop order restated in csrc/ge_heuristics.cu)."""
-        if self.kind in (0, 1, 6):
+        if self.kind in (0, 1, 6, 8):
             return True
         if self.kind == 2:
             return p["n_dests"] == 1 or p["n_dests"] == p["n_nodes"] - 1
@@ -70,6 +70,10 @@ ENV_SPECS = {
     "DistributionCenter-v0": EnvSpec(7, 5, 1, "node", "f64", False, True, True,
                                      (("weighted", True), ("max_distance", 1), ("target_count", -1),
                                       ("return_graph_obs", False), ("is_eval_env", False), ("parenting", 2))),
+    # graph_envs/perishable_product_delivery.py:26
+    "PerishableProductDelivery-v0": EnvSpec(8, 16, 1, "node", "f64", True, False, False,
+                                            (("n_products", 3), ("delivery_time", -1), ("weighted", True), ("return_graph_obs", False),
+                                             ("is_eval_env", False), ("parenting", -1))),
 }
 
 
@@ -126,6 +130,19 @@ def check_ctor_args(env_id, n_nodes, n_edges, kwargs):
             raise ValueError("Invalid parenting type")                              # multicast_routing.py:34-35
         if n_edges == -1:
             n_edges = _density_edges(n_nodes)
+    elif env_id == "PerishableProductDelivery-v0":
+        assert par in [1], "Parenting must be 1!"                                   # perishable_product_delivery.py:29
+        assert p["n_products"] <= 5, "Max 5 products!"                              # :34
+        if n_edges == -1:
+            n_edges = _density_edges(n_nodes)                                        # :48-49
+        # :51-58 -- the delivery-time range exists only for delivery_time == -1 (any other value makes the reference's
+        # reset() fail on the missing attribute)
+        assert p["delivery_time"] == -1, "PerishableProductDelivery: only delivery_time=-1 is usable in the reference"
+        avg_degree = 2 * n_edges / n_nodes
+        avg_dist = math.log(n_nodes) / math.log(avg_degree)
+        if p["weighted"]:
+            avg_dist = avg_dist * (0.3 + 1.0) / 2.0
+        p["dt_mn"], p["dt_mx"] = avg_dist * 0.6, avg_dist * 1.4
     elif env_id == "DistributionCenter-v0":
         assert par in [1, 2]                                                         # distribution_center.py:32
         if p["target_count"] == -1:

@@ -18,7 +18,8 @@
  *   ge_step           Env.step() + Env._get_mask() for the 8 envs
  *                     (shortest_path.py:105-141, longest_path.py:125-196, steiner_tree.py:116-157,
  *                      tsp.py:174-258, max_independent_set.py:92-124, densest_subgraph.py:105-196,
- *                      multicast_routing.py:155-266, distribution_center.py:129-174)
+ *                      multicast_routing.py:155-266, distribution_center.py:129-174,
+ *                      perishable_product_delivery.py:175-271)
  *   ge_obs_flat       utils.vectorize_graph (utils.py:87-88), layout of utils.devectorize_graph
  *   ge_obs_graph      utils.devectorize_graph (utils.py:14-23) applied on the device: (x, edge_features, edge_index)
  *   ge_features       feature_extraction.generate_features (feature_extraction.py:6-37)
@@ -50,7 +51,10 @@ typedef enum {
     GE_MAX_INDEPENDENT_SET = 4,/* MaxIndependentSet-v0   max_independent_set.py  node actions */
     GE_DENSEST_SUBGRAPH = 5,   /* DensestSubgraph-v0     densest_subgraph.py     node actions */
     GE_MULTICAST_ROUTING = 6,  /* MulticastRouting-v0    multicast_routing.py    edge actions */
-    GE_DISTRIBUTION_CENTER = 7 /* DistributionCenter-v0  distribution_center.py  node actions */
+    GE_DISTRIBUTION_CENTER = 7,/* DistributionCenter-v0  distribution_center.py  node actions */
+    GE_PERISHABLE_DELIVERY = 8 /* PerishableProductDelivery-v0  perishable_product_delivery.py  node actions (action == head: pick up).
+                                  n_dests = n_products (<= 5), targets = [B, 2 * n_products] pickups then dropoffs,
+                                  max_dist32 = delivery time; counters[b] = {2-bit status per product, moves made} */
 } ge_kind;
 
 typedef enum {

@@ -90,6 +90,10 @@ def run_case(env_id, kwargs, seed, policy, max_steps=100000):
         meta["heuristic"] = float(env.approx_solution)
     if hasattr(env, "n_choices"):
         meta["n_choices"] = float(env.n_choices)
+    if hasattr(env, "pickups"):           # PerishableProductDelivery
+        rec["pickups"] = np.asarray(env.pickups, dtype=np.int32)
+        rec["dropoffs"] = np.asarray(env.dropoffs, dtype=np.int32)
+        meta["delivery_time"] = float(env.delivery_time)
     if hasattr(env, "in_range_dict"):
         tg = sorted(int(t) for t in env.in_range_dict)
         rec["targets"] = np.array(tg, dtype=np.int32)
@@ -237,13 +241,24 @@ def cases():
         out.append((DC, dict(n_nodes=40, n_edges=120, parenting=p, max_distance=0.7, target_count=10), 2, "random"))
     out.append((DC, dict(n_nodes=70, n_edges=280, parenting=2, weighted=False, max_distance=2), 0, "random"))
     out.append((DC, dict(n_nodes=100, n_edges=500, parenting=2, max_distance=1), 0, "random"))
+    PP = "PerishableProductDelivery-v0"
+    for s in range(3):
+        out.append((PP, dict(n_nodes=10, n_edges=20, n_products=3, parenting=1, is_eval_env=True), s, "random"))
+    out.append((PP, dict(n_nodes=10, n_edges=20, n_products=3, parenting=1, is_eval_env=True), 0, "lowest"))
+    out.append((PP, dict(n_nodes=30, n_edges=90, n_products=5, parenting=1, is_eval_env=True), 1, "random"))
+    out.append((PP, dict(n_nodes=60, n_edges=200, n_products=2, parenting=1), 2, "random"))
+    out.append((PP, dict(n_nodes=20, n_edges=-1, n_products=1, weighted=False, parenting=1, is_eval_env=True), 3, "random"))
+    out.append((PP, dict(n_nodes=70, n_edges=160, n_products=4, parenting=1, is_eval_env=True), 0, "random"))
     return out
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     by_env = {}
+    only = set(sys.argv[1:])            # optional: regenerate just these env ids
     for env_id, kw, seed, pol in cases():
+        if only and env_id not in only:
+            continue
         meta, rec = run_case(env_id, kw, seed, pol)
         by_env.setdefault(env_id, []).append((meta, rec))
     versions = {"numpy": np.__version__, "networkx": nx.__version__, "python": sys.version.split()[0]}

@@ -16,7 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { K_SP = 0, K_LP = 1, K_ST = 2, K_TSP = 3, K_MIS = 4, K_DS = 5, K_MC = 6, K_DC = 7 };
+enum { K_SP = 0, K_LP = 1, K_ST = 2, K_TSP = 3, K_MIS = 4, K_DS = 5, K_MC = 6, K_DC = 7, K_PPD = 8 };
+#define PPD_MAXP 5   /* perishable_product_delivery.py:38-41: HAS_P = cols 1..5, NEEDS_P = 6..10, TIME_LEFT = 11..15 */
 #define NSTRUCT 5
 
 typedef struct {
@@ -56,6 +57,7 @@ static int dyn_cols(int kind) {
     case K_TSP: case K_MC: return 4;
     case K_DS: return 1;
     case K_DC: return 5;
+    case K_PPD: return 1 + 3 * PPD_MAXP;
     }
     return 0;
 }
@@ -278,6 +280,13 @@ static void mask_dc(const oenv *e, uint8_t *mask) { /* distribution_center.py:12
     for (int v = 0; v < N; ++v) if (ND(e, v, 1) == 1.0f) mask[v] = 0;
 }
 
+static void mask_ppd(const oenv *e, uint8_t *mask) { /* perishable_product_delivery.py:175-196 (parenting must be 1) */
+    memset(mask, 0, (size_t)e->N);
+    for (int i = 0; i < e->n_dests; ++i)
+        if (ND(e, e->head, 1 + i) == 1.0f) mask[e->head] = 1;               /* a product waits at the head: "pick up" = head */
+    for (int i = e->row_ptr[e->head]; i < e->row_ptr[e->head + 1]; ++i) mask[DST(e, i)] = 1;
+}
+
 int oenv_mask_len(const oenv *e) { return (e->kind == K_ST || e->kind == K_MC) ? e->M : e->N; }
 
 void oenv_mask(const oenv *e, uint8_t *mask) {
@@ -290,6 +299,7 @@ void oenv_mask(const oenv *e, uint8_t *mask) {
     case K_DS: mask_ds(e, mask); break;
     case K_MC: mask_mc(e, mask); break;
     case K_DC: mask_dc(e, mask); break;
+    case K_PPD: mask_ppd(e, mask); break;
     }
 }
 
@@ -359,6 +369,17 @@ oenv *oenv_create(int kind, int N, int M, int parenting, const int32_t *links, c
         for (int i = 0; i < e->n_dests; ++i) ND(e, dests[i], 1) = 1;
         for (int v = 0; v < N; ++v) { ND(e, v, 2) = (float)e->max_distance; ND(e, v, 3) = -1; }
         ND(e, 0, 3) = 0;
+        break;
+    case K_PPD:  /* perishable_product_delivery.py:120-133; dests = pickups[n] then dropoffs[n]; max_distance = delivery_time */
+        e->targets = malloc(sizeof(int32_t) * 2 * PPD_MAXP);
+        for (int i = 0; i < e->n_dests; ++i) {
+            e->targets[i] = dests[i]; e->targets[PPD_MAXP + i] = dests[e->n_dests + i];
+            ND(e, dests[i], 1 + i) = 1;
+            ND(e, dests[e->n_dests + i], 1 + PPD_MAXP + i) = 1;
+            for (int v = 0; v < N; ++v) ND(e, v, 1 + 2 * PPD_MAXP + i) = (float)e->max_distance;
+        }
+        e->head = 0;
+        ND(e, 0, 0) = 1;
         break;
     case K_DC: {
         e->targets = malloc(sizeof(int32_t) * (size_t)(e->n_targets > 0 ? e->n_targets : 1));
@@ -561,6 +582,50 @@ static void step_dc(oenv *e, int a, ostep *r, uint8_t *mask) { /* distribution_c
     r->reward = reward;
 }
 
+static void step_ppd(oenv *e, int a, ostep *r, uint8_t *mask) { /* perishable_product_delivery.py:198-271 */
+    const int N = e->N, P = e->n_dests;
+    if (!(a >= 0 && a < N)) FAIL(r);
+    mask_ppd(e, mask);
+    if (!mask[a]) FAIL(r);
+    double reward = 0;
+    r->heuristic = e->heuristic;            /* info every step (:210-212); solution_cost is the value BEFORE this move */
+    r->solution_cost = e->cost;
+    if (a == e->head) {                     /* pick up (:214-221): the one product waiting here goes into transit */
+        int prod = -1;
+        for (int i = 0; i < PPD_MAXP; ++i) if (ND(e, e->head, 1 + i) == 1.0f) { prod = i; break; }
+        for (int v = 0; v < N; ++v) ND(e, v, 1 + prod) = -1;
+        reward += 2;
+        e->steps_taken++;
+    } else {                                /* move (:223-249) */
+        reward = -adj_lookup(e, e->head, a);
+        e->cost -= reward;
+        e->steps_taken++;
+        ND(e, e->head, 0) = 0; ND(e, a, 0) = 1;
+        e->head = a;
+        for (int i = 0; i < P; ++i) {
+            if (ND(e, e->head, 1 + i) == -1.0f) {
+                const float dt = (float)adj_lookup(e, e->head, a);   /* self.adj[self.head, action] AFTER head = action: adj[a, a] = 0 (:234) */
+                float sum = 0;                                       /* numpy float32 pairwise sum; only its sign matters */
+                for (int v = 0; v < N; ++v) { ND(e, v, 1 + 2 * PPD_MAXP + i) -= dt; sum += ND(e, v, 1 + 2 * PPD_MAXP + i); }
+                if (sum < 0 - 1e-6) {                                /* :236-241 early return, no mask */
+                    r->done = 1; r->reward = -2.0 * N * P; r->solved = 0; r->has_mask = 0;
+                    return;
+                }
+                if (ND(e, e->head, 1 + PPD_MAXP + i) == 1.0f) {      /* delivered (:243-249) */
+                    reward += 2;
+                    for (int v = 0; v < N; ++v) { ND(e, v, 1 + i) = 0; ND(e, v, 1 + PPD_MAXP + i) = 0; ND(e, v, 1 + 2 * PPD_MAXP + i) = 0; }
+                }
+            }
+        }
+    }
+    double has = 0;
+    for (int v = 0; v < N; ++v) for (int i = 0; i < PPD_MAXP; ++i) has += ND(e, v, 1 + i);
+    if (has == 0) { r->done = 1; r->solved = 1; reward += 2.0 * N; }                                   /* :252-255 */
+    else if (e->steps_taken >= N * P * 50) { r->done = 1; r->solved = 0; reward = -2.0 * N * P; }      /* :256-259 */
+    mask_ppd(e, mask); r->has_mask = 1;
+    r->reward = reward;
+}
+
 /* mask_out receives info['mask'] when has_mask (length oenv_mask_len). */
 void oenv_step(oenv *e, int action, ostep *r, uint8_t *mask_out) {
     r->reward = 0; r->solution_cost = NAN; r->heuristic = NAN;
@@ -574,6 +639,7 @@ void oenv_step(oenv *e, int action, ostep *r, uint8_t *mask_out) {
     case K_DS: step_ds(e, action, r, mask_out); break;
     case K_MC: step_mc(e, action, r, mask_out); break;
     case K_DC: step_dc(e, action, r, mask_out); break;
+    case K_PPD: step_ppd(e, action, r, mask_out); break;
     }
     if (r->status == 0 && r->done) e->done = 1;
 }
@@ -606,6 +672,15 @@ void oenv_reset_state(oenv *e) {
         for (int i = 0; i < e->M; ++i) ED(e, i, 1) = 0;
         break;
     case K_DC: for (int v = 0; v < N; ++v) { ND(e, v, 1) = 0; ND(e, v, 3) = 0; } break;
+    case K_PPD:
+        for (int v = 0; v < N; ++v) for (int c = 0; c < 1 + 3 * PPD_MAXP; ++c) ND(e, v, c) = 0;
+        for (int i = 0; i < e->n_dests; ++i) {
+            ND(e, e->targets[i], 1 + i) = 1;
+            ND(e, e->targets[PPD_MAXP + i], 1 + PPD_MAXP + i) = 1;
+            for (int v = 0; v < N; ++v) ND(e, v, 1 + 2 * PPD_MAXP + i) = (float)e->max_distance;
+        }
+        e->head = 0; ND(e, 0, 0) = 1;
+        break;
     }
     (void)dc;
 }

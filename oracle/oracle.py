@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(_HERE, "libgraphenvs_oracle.so")
 KINDS = {
     "ShortestPath-v0": 0, "LongestPath-v0": 1, "SteinerTree-v0": 2, "TSP-v0": 3,
     "MaxIndependentSet-v0": 4, "DensestSubgraph-v0": 5, "MulticastRouting-v0": 6,
-    "DistributionCenter-v0": 7,
+    "DistributionCenter-v0": 7, "PerishableProductDelivery-v0": 8,
 }
 EDGE_ACTION = {2, 6}
 
@@ -88,6 +88,8 @@ class OracleEnv:
         n_targets = 0
         if self.kind == 7:
             n_targets = 0 if dests is None else dests.shape[0]
+        if self.kind == 8:      # dests = pickups then dropoffs; n_dests = n_products; max_distance = delivery_time
+            n_dests = dests.shape[0] // 2
         ip = np.array([src, dest, n_dests, n_choices, n_targets, 0], dtype=np.int32)
         dp = np.array([max_distance, heuristic], dtype=np.float64)
         nc = None if node_cost is None else np.ascontiguousarray(node_cost, dtype=np.float64)

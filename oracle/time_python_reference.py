@@ -34,6 +34,7 @@ CONFIGS = [
     ("cfg5_multicast", "MulticastRouting-v0", dict(n_nodes=500, n_edges=4000, n_dests=3, parenting=4)),
     ("cfg5_distcenter", "DistributionCenter-v0", dict(n_nodes=500, n_edges=4000, parenting=2, target_count=100, max_distance=1)),
     ("densest", "DensestSubgraph-v0", dict(n_nodes=500, n_edges=4000, parenting=1)),
+    ("perishable", "PerishableProductDelivery-v0", dict(n_nodes=50, n_edges=200, n_products=3, parenting=1)),
 ]
 
 
@@ -76,7 +77,10 @@ def main():
     import networkx
     out["networkx"] = networkx.__version__
     out["numpy"] = np.__version__
+    only = set(sys.argv[2:])                      # optional: time just these configs and merge them into the file given as --merge
     for name, env_id, kw in CONFIGS:
+        if only and name not in only:
+            continue
         s, ts, r, tr = loop(env_id, kw, budget, 0)
         with mp.Pool(cores) as pool:
             res = pool.map(_worker, [(env_id, kw, budget, 1000 * (i + 1)) for i in range(cores)])

@@ -8,10 +8,10 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ENV_IDS = ["ShortestPath-v0", "LongestPath-v0", "SteinerTree-v0", "TSP-v0", "MaxIndependentSet-v0",
-           "DensestSubgraph-v0", "MulticastRouting-v0", "DistributionCenter-v0"]
+           "DensestSubgraph-v0", "MulticastRouting-v0", "DistributionCenter-v0", "PerishableProductDelivery-v0"]
 DYN_COLS = {"ShortestPath-v0": 2, "LongestPath-v0": 2, "SteinerTree-v0": 2, "TSP-v0": 4,
             "MaxIndependentSet-v0": 2, "DensestSubgraph-v0": 1, "MulticastRouting-v0": 4,
-            "DistributionCenter-v0": 5}
+            "DistributionCenter-v0": 5, "PerishableProductDelivery-v0": 16}
 
 
 def load_cases(env_id):
@@ -63,4 +63,7 @@ def instance_kwargs(m, r):
     elif env_id == "DistributionCenter-v0":
         d.update(dests=r["targets"], node_cost=nodes0[:, 0].astype(np.float64),
                  max_distance=float(kw.get("max_distance", 1)))
+    elif env_id == "PerishableProductDelivery-v0":
+        d.update(dests=np.concatenate([r["pickups"], r["dropoffs"]]).astype(np.int32), n_dests=len(r["pickups"]),
+                 max_distance=float(m["delivery_time"]))
     return d

@@ -111,5 +111,8 @@ def test_env_info_table_and_vectorize_roundtrip():
 def test_registry_ids():
     from graphenvs_b200 import registration
     assert sorted(registration.registry) == sorted(spec.ENV_SPECS)
+    assert "PerishableProductDelivery-v0" in registration.registry      # round 2: the ninth reference id
     with pytest.raises(KeyError):
-        registration.make("PerishableProductDelivery-v0", n_nodes=5, n_edges=6)
+        registration.make("NoSuchEnv-v0", n_nodes=5, n_edges=6)
+    with pytest.raises(AssertionError):                                   # perishable_product_delivery.py:29
+        spec.check_ctor_args("PerishableProductDelivery-v0", 10, 20, {"parenting": 2})

@@ -22,6 +22,7 @@ def _fake_env(wl):
     d.kind, d.B, d.N, d.M = ENV_SPECS[env_id].kind, 4, N, 2 * E
     d.parenting = kw.get("parenting", -1)
     d.n_targets = kw.get("target_count", 0)
+    d.n_dests = kw.get("n_dests", kw.get("n_products", 0))
     _native.lib().ge_fill_layout(C.byref(d))
     return types.SimpleNamespace(desc=d, N=N, M=2 * E, env_id=env_id, t={"mask_bytes": 1})
 

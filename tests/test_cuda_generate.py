@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import cuda_util as cu
 from graphenvs_b200 import BatchedGraphEnv
 
 pytestmark = pytest.mark.gpu
@@ -21,6 +22,7 @@ CFG = [
     ("DensestSubgraph-v0", 60, 200, {"parenting": 1}),
     ("MulticastRouting-v0", 120, 600, {"n_dests": 5, "parenting": 4}),
     ("DistributionCenter-v0", 100, 400, {"parenting": 2}),
+    ("PerishableProductDelivery-v0", 50, 200, {"n_products": 3, "parenting": 1}),
 ]
 
 
@@ -81,6 +83,13 @@ def test_generated_instances_are_valid(cfg):
             assert set(ins.node_cost.tolist()) <= {1.0, 2.0, 3.0}
         if env_id == "MaxIndependentSet-v0":
             assert set(np.round(ins.node_cost * 10).astype(int)) <= set(range(3, 10))
+        if env_id == "PerishableProductDelivery-v0":          # perishable_product_delivery.py:96-114
+            P = kw["n_products"]
+            assert len(set(ins.dests.tolist())) == 2 * P, "pickups and dropoffs are distinct nodes"
+            assert env.params["dt_mn"] - 1e-6 <= ins.max_distance <= env.params["dt_mx"] + 1e-6
+            oe = cu.oracle_from_instance(env_id, ins, env.params)
+            for i in range(P):
+                assert oe.sssp(int(ins.dests[i]))[int(ins.dests[P + i])] < ins.max_distance + 1e-5, "dropoff within the delivery time of its pickup"
     # distribution sanity: weights roughly uniform over the 7 values (B*E draws)
     if env_id in ("LongestPath-v0", "SteinerTree-v0") and N >= 50:
         allw = np.concatenate([np.round(i.w64 * 10).astype(int) for i in inst])

@@ -59,6 +59,9 @@ CONFIGS = [
     ("MulticastRouting-v0", 40, 120, {"parenting": 1, "n_dests": 3}, 20),
     ("DistributionCenter-v0", 120, 500, {"parenting": 2}, 40),
     ("DistributionCenter-v0", 90, 300, {"parenting": 1, "max_distance": 1.2}, 40),
+    ("PerishableProductDelivery-v0", 40, 100, {"n_products": 3, "parenting": 1}, 400),
+    ("PerishableProductDelivery-v0", 300, 900, {"n_products": 5, "parenting": 1}, 300),
+    ("PerishableProductDelivery-v0", 12, 20, {"n_products": 5, "parenting": 1, "weighted": False}, 3200),   # runs into max_steps = N * P * 50
 ]
 
 
