@@ -66,8 +66,8 @@ class BatchedGraphEnv:
             B32 = (B + 31) // 32 * 32                             # whole tiles of 32 envs for the N <= 64 layout
             self._adj_store = z((B32 * d.ADJS,), torch.int32)
             T["adj_bits"] = self._adj_store
-            if env_id == "PerishableProductDelivery-v0":
-                pass                                                  # looks its one edge weight up in the CSR row
+            if env_id == "PerishableProductDelivery-v0" and (N > 64 or force_warp):
+                pass                                                  # warp-per-env kernel: looks its one edge weight up in the CSR row
             elif N <= 64 and self.spec.step_w == "f64":
                 T["wmat"] = z((B, N, N), torch.float64)              # dense fp64 weights for the lane-per-env kernels
             elif self.spec.step_w == "f64":

@@ -498,6 +498,7 @@ int ge_dc_build_transposed(const ge_batch *d, cudaStream_t st);
 // PerishableProductDelivery (ge_ppd.cu)
 int ge_ppd_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st);
 int ge_ppd_reset(const ge_batch *d, const uint8_t *select, cudaStream_t st);
+bool ge_ppd_lane(const ge_batch *d);
 // eval heuristic kernels (ge_heuristics.cu)
 int ge_heuristics_launch(const ge_batch *d, int what, cudaStream_t st);
 
@@ -763,7 +764,7 @@ const char *ge_step_kernel_name(const ge_batch *d, int sampled) {
     if (!d) return "";
     const char *fam;
     char shape[48] = "";
-    if (d->kind == GE_PERISHABLE_DELIVERY) { fam = "ppd_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }
+    if (d->kind == GE_PERISHABLE_DELIVERY) { fam = ge_ppd_lane(d) ? "ppd_lane_step_kernel" : "ppd_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d", sampled); }
     else if (ge_lane_eligible(d)) { fam = "lane_step_kernel"; snprintf(shape, sizeof(shape), "STAGED=%d,SAMPLED=%d", (d->kind == GE_LONGEST_PATH || d->kind == GE_TSP) && d->parenting >= 2, sampled); }
     else if (ge_group_eligible(d)) { fam = "group_step_kernel"; snprintf(shape, sizeof(shape), "SAMPLED=%d,G=%d", sampled, d->NW <= 8 ? 8 : d->NW <= 16 ? 16 : 32); }
     else if (ge_incr_eligible(d)) {

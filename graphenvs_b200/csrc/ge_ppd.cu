@@ -141,6 +141,120 @@ __global__ void __launch_bounds__(GE_WPB * 32) ppd_step_kernel(ge_batch d, int32
     }
 }
 
+// N <= 64: one LANE per env (like ge_lane.cu): the mask is one 64-bit register, the edge weight one load from the dense
+// wmat, the next mask one adjacency row.  A warp per env spent a whole warp on a 50-node graph (75 us per 65,536-env step).
+template <bool SAMPLED>
+__global__ void __launch_bounds__(128) ppd_lane_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out, uint64_t seed, uint32_t t) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    const int N = d.N, P = d.n_dests, NW = d.NW;
+    const int32_t *tg = d.targets + (size_t)b * d.n_targets;
+    const uint32_t nsteps = d.env_steps ? d.env_steps[b] : 0u;
+    int4 c = *reinterpret_cast<const int4 *>(d.counters + (size_t)b * 4);
+    int head = d.head[b];
+    double cost = d.cost[b];
+    const bool was_done = d.done[b] != 0;
+    u64 oldm = NW == 1 ? (u64)d.mask_bits[b] : ((u64)d.mask_bits[2 * (size_t)b] | ((u64)d.mask_bits[2 * (size_t)b + 1] << 32));
+    int pk[PPD_MAXP], dr[PPD_MAXP];
+#pragma unroll
+    for (int i = 0; i < PPD_MAXP; ++i) { pk[i] = i < P ? tg[i] : -1; dr[i] = i < P ? tg[P + i] : -1; }
+    int a;
+    if (SAMPLED) {
+        const int total = __popcll(oldm);
+        a = -1;
+        if (total > 0) {
+            const uint32_t r = (uint32_t)(((uint64_t)mix32(seed, (uint32_t)(d.env_id0 + b), t + nsteps) * (uint64_t)total) >> 32);
+            const uint32_t lo = (uint32_t)oldm, hi = (uint32_t)(oldm >> 32);
+            const int clo = __popc(lo);
+            a = (int)r < clo ? nth_set_bit(lo, (int)r) : 32 + nth_set_bit(hi, (int)r - clo);
+        }
+        actions[b] = a;
+    } else {
+        a = actions[b];
+    }
+    double reward = 0.0, sol = __longlong_as_double(0x7ff8000000000000ll);
+    int done = 0, solved = -1, has_mask = 1, status = GE_STEP_OK;
+    bool write_state = false;
+    if (was_done) {
+        has_mask = 0; status = GE_STEP_AFTER_DONE;
+    } else if (!(a >= 0 && a < N && ((oldm >> a) & 1ull))) {
+        status = GE_STEP_INVALID; has_mask = 0;
+    } else {
+        write_state = true;
+        sol = cost;
+        if (a == head) {
+#pragma unroll
+            for (int i = 0; i < PPD_MAXP; ++i)
+                if (i < P && ((c.x >> (2 * i)) & 3) == 0 && pk[i] == head) { c.x |= 1 << (2 * i); break; }
+            reward = 2.0;
+            c.y += 1;
+        } else {
+            const double w = __ldg(d.wmat + ((size_t)b * N + head) * N + a);
+            reward = -w;
+            cost = cost - reward;
+            c.y += 1;
+            head = a;
+            const float tl = d.max_dist32[b];
+#pragma unroll
+            for (int i = 0; i < PPD_MAXP; ++i) {
+                if (i >= P || ((c.x >> (2 * i)) & 3) != 1) continue;
+                if ((float)N * tl < 0.f - 1e-6f) { done = 1; reward = -2.0 * N * P; solved = 0; has_mask = 0; break; }
+                if (dr[i] == head) { reward += 2.0; c.x = (c.x & ~(3 << (2 * i))) | (2 << (2 * i)); }
+            }
+        }
+        if (has_mask) {
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < PPD_MAXP; ++i) all &= i >= P || ((c.x >> (2 * i)) & 3) == 2;
+            if (all) { done = 1; solved = 1; reward += 2.0 * N; }
+            else if (c.y >= N * P * 50) { done = 1; solved = 0; reward = -2.0 * N * P; }
+        }
+    }
+    out.reward[b] = (float)reward;
+    ge_step_flags f;
+    f.done = (uint8_t)done; f.solved = (int8_t)solved; f.status = (uint8_t)status; f.has_mask = (uint8_t)has_mask;
+    out.flags[b] = f;
+    out.solution_cost[b] = sol;
+    if (d.traj) {
+        const u64 cs = d.traj[b];
+        d.traj[b] = ((cs << 7) | (cs >> 57)) ^ (u64)(uint32_t)a ^ ((u64)done << 40) ^ ((u64)(solved & 3) << 44) ^ ((u64)status << 48);
+    }
+    if (status == GE_STEP_OK) {
+        if (d.env_steps) d.env_steps[b] = nsteps + 1u;
+        d.acc[2 * (size_t)d.acc_stride + b] += reward;
+        if (done) {
+            d.acc[b] += 1.0;
+            if (solved == 1) d.acc[(size_t)d.acc_stride + b] += 1.0;
+            if (sol == sol) d.acc[3 * (size_t)d.acc_stride + b] += sol;
+        }
+    }
+    if (!write_state) return;
+    const bool auto_reset = done && (d.flags & GE_FLAG_AUTO_RESET);
+    if (auto_reset) { head = 0; cost = 0.0; c = make_int4(0, 0, 0, 0); }
+    if (has_mask || auto_reset) {
+        const uint32_t *row = d.adj_bits + (size_t)b * d.ADJS + (size_t)head * NW;
+        u64 m = NW == 1 ? (u64)row[0] : ((u64)row[0] | ((u64)row[1] << 32));
+        bool waiting = false;
+#pragma unroll
+        for (int i = 0; i < PPD_MAXP; ++i) waiting |= i < P && ((c.x >> (2 * i)) & 3) == 0 && pk[i] == head;
+        if (waiting) m |= 1ull << head;
+        if (NW == 1) d.mask_bits[b] = (uint32_t)m;
+        else { d.mask_bits[2 * (size_t)b] = (uint32_t)m; d.mask_bits[2 * (size_t)b + 1] = (uint32_t)(m >> 32); }
+        if (d.mask_mirror) { for (int w = 0; w < NW; ++w) d.mask_mirror[(size_t)b * NW + w] = (uint32_t)(m >> (32 * w)); }
+        if (d.mask_bytes) {
+            uint4 *mb = reinterpret_cast<uint4 *>(d.mask_bytes + (size_t)b * d.AP);
+            for (int k = 0; k < (d.AP >> 4); ++k) {
+                const uint32_t bits = (uint32_t)(m >> (16 * k)) & 0xffffu;
+                mb[k] = make_uint4(expand4(bits), expand4(bits >> 4), expand4(bits >> 8), expand4(bits >> 12));
+            }
+        }
+    }
+    d.head[b] = head;
+    d.cost[b] = cost;
+    *reinterpret_cast<int4 *>(d.counters + (size_t)b * 4) = c;
+    if (done && !auto_reset) d.done[b] = 1;
+}
+
 __global__ void __launch_bounds__(GE_WPB * 32) ppd_reset_kernel(ge_batch d, const uint8_t *__restrict__ select) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
@@ -168,9 +282,17 @@ int ge_ppd_check(const ge_batch *d) {
     return GE_OK;
 }
 
+bool ge_ppd_lane(const ge_batch *d) { return d->N <= 64 && d->wmat != nullptr && !(d->flags & GE_FLAG_FORCE_WARP); }
+
 int ge_ppd_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st) {
     int rc = ge_ppd_check(d);
     if (rc) return rc;
+    if (ge_ppd_lane(d)) {
+        const int T = 128, blocks = (d->B + T - 1) / T;
+        if (sampled) ppd_lane_step_kernel<true><<<blocks, T, 0, st>>>(*d, actions, *out, seed, t);
+        else ppd_lane_step_kernel<false><<<blocks, T, 0, st>>>(*d, actions, *out, seed, t);
+        return ppd_launched("ppd_lane_step_kernel");
+    }
     const int blocks = (d->B + GE_WPB - 1) / GE_WPB;
     if (sampled) ppd_step_kernel<true><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
     else ppd_step_kernel<false><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);

@@ -8,7 +8,7 @@ The reference needs networkx and /root/reference, neither of which exists on the
 beside the GPU numbers; bench.py carries the committed result file as `cpu_reference_python` with its date,
 host and core count stated.
 
-    python oracle/time_python_reference.py [seconds per config, default 6] > profiles/r02_python_reference_cpu.json
+    python oracle/time_python_reference.py [seconds per config, default 6] [config names ...] > profiles/r02_python_reference_cpu.json
 """
 import json
 import multiprocessing as mp
@@ -77,7 +77,7 @@ def main():
     import networkx
     out["networkx"] = networkx.__version__
     out["numpy"] = np.__version__
-    only = set(sys.argv[2:])                      # optional: time just these configs and merge them into the file given as --merge
+    only = set(sys.argv[2:])                      # optional: time just these configs
     for name, env_id, kw in CONFIGS:
         if only and name not in only:
             continue

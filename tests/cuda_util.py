@@ -17,6 +17,8 @@ def has_fast_path(env_id, n_nodes, parenting=None):
         return True
     if env_id in ("ShortestPath-v0", "DensestSubgraph-v0", "LongestPath-v0", "TSP-v0"):
         return True   # group-per-env kernels (64 < N <= 1024)
+    if env_id == "PerishableProductDelivery-v0":
+        return n_nodes <= 64   # lane-per-env kernel vs the warp-per-env one
     if env_id in ("SteinerTree-v0", "MaxIndependentSet-v0", "DistributionCenter-v0"):
         return True   # (DistributionCenter: exact distance automaton vs the fp64 search)
     return env_id == "MulticastRouting-v0" and (parenting is None or parenting >= 2)
