@@ -68,6 +68,7 @@ def layout_bytes_per_step(env):
     incremental = not (d.flags & 8) and (k in ("SteinerTree-v0",) or (k == "MulticastRouting-v0" and d.parenting >= 2)
                                          or (k == "MaxIndependentSet-v0" and N > 64))
     if incremental:
+        has_bytes = False                                  # round 2: the incremental kernels keep only the packed mask current
         sample = d.AW * 4                                  # the sampler walks the packed mask
         if k == "MaxIndependentSet-v0":
             return float(fixed + sample + 2 * 8 + 4 + 32 + (1 if has_bytes else 0))
@@ -75,7 +76,7 @@ def layout_bytes_per_step(env):
         graph = 8 + 8 + deg * 8                            # col[a], w[a]; rp[v], rp[v+1]; row(v): col + rev / w
         state = nw4 + 8 + 4 + 32                           # tree bits read, one word r/w, target word, counters r/w
         if k == "MulticastRouting-v0":
-            graph += 4 + 4 + 4 + 8 + 4                     # esrc[a], dist[u], dist[v] write, edge bit r/w, max_distance
+            graph += 8 + 4 + 8 + 4                         # best[v] (the joining node's distance), dist[v] write, edge bit r/w, max_distance
             if d.parenting >= 3:
                 graph += deg * (8 + 4)                     # best[x] read (+ write for about half of them)
         return float(fixed + sample + upd + graph + state)
@@ -99,8 +100,10 @@ def layout_bytes_per_step(env):
         # cutoff SSSP ball: with cutoff c and smallest weight w only nodes within c - w are expanded; measured ~22 rows
         # at N=500 E=4000 c=1; each row = 2 row_ptr + deg * (col 4 + w64 8); + in-range rows of the
         # still uncovered targets (about half of them on average) + covered/taken/target sets
-        rows = 22 if (N == 500 and M == 8000) else max(1.0, min(N, 1 + deg + deg * deg * 0.06))
-        graph = rows * (8 + deg * 12) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
+        # round 2 (csrc/ge_dc.cu): ~27 rows are expanded at N=500 E=4000 c=1, and of a weight-sorted row only the prefix that
+        # can stay within the cutoff is read (~45 % of it), 4 bytes per edge (col | code)
+        rows = 27 if (N == 500 and M == 8000) else max(1.0, min(N, 1 + deg + deg * deg * 0.06))
+        graph = rows * (8 + 0.45 * deg * 4) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
     elif k == "DensestSubgraph-v0":
         graph = nw4 + 16 + 2 * nw4
     elif k == "PerishableProductDelivery-v0":
@@ -598,8 +601,25 @@ def turnover_costs(D, K=300):
     return out
 
 
+def pin_rank_to_cores(args):
+    """One disjoint block of host cores per rank (N > 1): the ranks' launch / completion-polling threads stop competing for
+    the same cores.  nvidia-smi topo on the test boxes lists ONE NUMA node and one affinity range for all eight GPUs, so
+    there is no closer choice than an even split of that range."""
+    world, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world <= 1 or args.no_pin or not hasattr(os, "sched_setaffinity"):
+        return None
+    cores = sorted(os.sched_getaffinity(0))
+    k = len(cores) // world
+    if k < 1:
+        return None
+    mine = cores[local * k:(local + 1) * k]
+    os.sched_setaffinity(0, mine)
+    return "%d-%d" % (mine[0], mine[-1])
+
+
 def run_ours(args):
     import torch
+    pinned = pin_rank_to_cores(args)
     D = Dist()
     rank, world = D.rank, D.world
     wl = args.workload
@@ -671,6 +691,7 @@ def run_ours(args):
             "cfg5_strong_scaling": cfg5,
             "feature_extraction_us_per_env": feats,
             "instance_turnover": turn,
+            "host_cores_of_rank0": pinned,
             "bench_wall_s": time.time() - t_all,
         }
         if "cpu_baseline" in head:
@@ -699,6 +720,7 @@ def main():
     ap.add_argument("--only-headline", action="store_true", help="skip the all-workloads pass, config 5 and the feature costs")
     ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--no-turnover", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not pin each rank to its own block of host cores")
     ap.add_argument("--no-e2e-obs", dest="e2e_obs", action="store_false")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
     ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],

@@ -1,22 +1,47 @@
 #!/usr/bin/env python
-"""Markdown table from a jsonl of bench.py lines:  python profiles/make_table.py profiles/r01_all_workloads.jsonl"""
+"""Markdown tables from ONE bench.py line (round 2: the default run carries every workload):
+    python profiles/make_table.py profiles/r02_bench_default.json [profiles/r02_scaling_1gpu.json ...2gpu.json ...]"""
 import json, sys
-rows = []
-for line in open(sys.argv[1]):
-    line = line.strip()
-    if not line:
-        continue
-    try:
-        d = json.loads(line)
-    except Exception:
-        continue
-    if "roofline" not in d:
-        continue
-    r, c = d["roofline"], d.get("cpu_baseline") or {}
-    rows.append((d["config"]["name"], d["config"]["envs_per_gpu"], d["value"], 1e3 * d["ms_per_step"], r["bytes_per_env_step"],
-                 r["achieved"], r["frac"], d["e2e"]["value"], c.get("value"), c.get("cores")))
-print("| workload | envs/GPU | env-steps/s (device) | µs / batch step | B / env-step (this layout) | achieved GB/s | frac of 6545 GB/s | e2e env-steps/s (host buffers) | CPU port env-steps/s (cores) | e2e ÷ CPU |")
-print("|---|---|---|---|---|---|---|---|---|---|")
-for n, B, v, us, by, gb, fr, e2e, cpu, cores in rows:
-    print("| %s | %d | %.3g | %.1f | %.0f | %.0f | %.3f | %.3g | %s | %s |" % (
-        n, B, v, us, by, gb, fr, e2e, ("%.3g (%s)" % (cpu, cores)) if cpu else "-", ("%.0fx" % (e2e / cpu)) if cpu else "-"))
+
+
+def load(path):
+    for line in open(path):
+        line = line.strip()
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except Exception:
+                pass
+    raise SystemExit("no JSON line in " + path)
+
+
+d = load(sys.argv[1])
+print("| workload | envs/GPU | env-steps/s (device) | µs / batch step | B / env-step (this layout) | measured DRAM B / env-step (ncu) | frac of %.0f GB/s | e2e env-steps/s (host buffers) | CPU port env-steps/s (cores) | Python reference, 1 core / all cores | e2e ÷ CPU port |"
+      % d["roofline"]["peak"])
+print("|---|---|---|---|---|---|---|---|---|---|---|")
+for w in d["workloads"]:
+    r, c, py = w["roofline"], w.get("cpu_baseline") or {}, w.get("cpu_reference_python") or {}
+    tr = r.get("traffic")
+    pyref = "-"
+    if py:
+        a, b = py.get("one_core_step_only_steps_per_s"), py.get("all_cores_steps_per_s")
+        pyref = "%s / %s (%s)" % ("%.3g" % a if a else "n/a", "%.3g" % b if b else "n/a", py.get("cores"))
+    print("| %s | %d | %.3g | %.1f | %.0f | %s | %.3f | %.3g | %s | %s | %s |" % (
+        w["name"], w["envs_per_gpu"], w["value"], 1e3 * w["ms_per_step"], r["bytes_per_env_step"],
+        ("%.0f" % (tr / w["envs_per_gpu"])) if tr else "-", r["frac"], w["e2e"]["value"],
+        ("%.3g (%s)" % (c["value"], c["cores"])) if c else "-", pyref, ("%.0fx" % (w["e2e"]["value"] / c["value"])) if c else "-"))
+if len(sys.argv) > 2:
+    print()
+    print("| GPUs | cfg2 env-steps/s (weak, 65,536 envs/GPU) | cfg2 e2e | cfg5 Multicast (524,288 envs total) | cfg5 DistributionCenter (524,288 total) | cfg5 all 1,048,576 envs, one step of both | envs per GPU and kind |")
+    print("|---|---|---|---|---|---|---|")
+    base = None
+    for p in sys.argv[2:]:
+        s = load(p)
+        c5 = s["cfg5_strong_scaling"]
+        row = (s["value"], s["e2e"]["value"], c5["cfg5_multicast"]["value"], c5["cfg5_distcenter"]["value"], c5["combined"]["value"])
+        if base is None:
+            base = row
+        n = s["n_gpus"]
+        print("| %d | %s | %d |" % (n, " | ".join("%.3g (%.2f)" % (v, v / (b * (n if i < 2 else n))) for i, (v, b) in enumerate(zip(row, base))),
+                                   c5["cfg5_multicast"]["envs_per_gpu"]))
+    print("\n(in parentheses: efficiency = value / (N x the 1-GPU value))")
