@@ -202,6 +202,46 @@ __device__ __forceinline__ int group_sample(const Grp<G> &g, const uint32_t *mb,
     return action;
 }
 
+// The same draw with the whole mask in REGISTERS: lane l of the group loads WPL consecutive words (AW <= G * WPL) up front --
+// independent loads, one memory round -- instead of walking the mask G words at a time with an early exit that makes every
+// trip wait for its own load (ncu r02: the walk was ~30 % of the instructions and 18 % of the stall samples of the Multicast
+// step, whose mask is 250 words).  `total` must be the mask's popcount (the incremental kernels track it).
+template <int G, int WPL>
+__device__ __forceinline__ int group_sample_regs(const Grp<G> &g, const uint32_t *mb, int AW, uint64_t seed, uint32_t env, uint32_t t, int total) {
+    if (total <= 0) return -1;
+    const uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
+    uint32_t w[WPL];
+    const int base = g.gl * WPL;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) w[k] = (base + k < AW) ? mb[base + k] : 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) cnt += __popc(w[k]);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        const int x = __shfl_up_sync(g.mask, inc, o, G);
+        if (g.gl >= o) inc += x;
+    }
+    const int excl = inc - cnt;
+    const bool mine = (int)r >= excl && (int)r < inc;
+    int rr = (int)r - excl, kk = 0;
+    uint32_t word = 0;
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+        const int c = __popc(w[k]);
+        if (!found) {
+            if (rr < c) { found = true; word = w[k]; kk = k; }
+            else rr -= c;
+        }
+    }
+    int a = (mine && found) ? (((base + kk) << 5) + nth_set_bit(word, rr)) : -1;
+    const unsigned hit = g.ballot(mine && found);
+    if (!hit) return -1;
+    return g.shfl(a, __ffs(hit) - 1);
+}
+
 // Publishes the mask built in shared memory: packed words, optional byte mask; returns popcount.
 __device__ inline int emit_mask(const ge_batch &d, int b, int lane, uint32_t *msk) {
     int cnt = 0;

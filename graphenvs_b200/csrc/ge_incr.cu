@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     const uint32_t tgw = (regs && lane < d.NW) ? tg[lane] : 0u;
     int a;
     if (SAMPLED) {
-        a = group_sample<G>(g, d.mask_bits + (size_t)b * d.AW, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
+        const uint32_t *mbits = d.mask_bits + (size_t)b * d.AW;
+        if (d.AW <= 4 * G) a = group_sample_regs<G, 4>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
+        else if (d.AW <= 16 * G) a = group_sample_regs<G, 16>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
+        else a = group_sample<G>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         if (lane == 0) actions[b] = a;
     } else {
         a = actions[b];
