@@ -75,20 +75,16 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
     const int grp = lane >> 3, gl = lane & 7;
     uint16_t *cur = s.cur, *nxt = s.nxt;
     while (ncur > 0) {
-        // Two-deep software pipeline over the trips of four rows: the row bounds are loaded two trips ahead and the first
-        // eight edges of every row one trip ahead, so the relaxations of a trip never wait for their own loads (the wait
-        // for edges[e] was 28 % of the stall samples of the one-deep version, profiles/r02_final_step_kernel_cfg5_distcenter.md).
-        int lo = 0, hi = 0, du = 0, lo_n = 0, hi_n = 0, du_n = 0;
+        int lo = 0, hi = 0, du = 0;                                     // bounds of the first four rows
         if (grp < ncur) { const int u = cur[grp]; lo = rp[u]; hi = rp[u + 1]; du = (int)s.q[u]; }
-        if (4 + grp < ncur) { const int u = cur[4 + grp]; lo_n = rp[u]; hi_n = rp[u + 1]; du_n = (int)s.q[u]; }
-        uint32_t pk = (lo + gl < hi) ? edges[lo + gl] : 0xffffffffu;
         for (int i0 = 0; i0 < ncur; i0 += 4) {
-            int lo_nn = 0, hi_nn = 0, du_nn = 0;
-            if (i0 + 8 + grp < ncur) { const int u = cur[i0 + 8 + grp]; lo_nn = rp[u]; hi_nn = rp[u + 1]; du_nn = (int)s.q[u]; }
-            const uint32_t pk_n = (lo_n + gl < hi_n) ? edges[lo_n + gl] : 0xffffffffu;
+            int lo_n = 0, hi_n = 0, du_n = 0;                          // next four rows, loaded while these are relaxed
+            if (i0 + 4 + grp < ncur) { const int u = cur[i0 + 4 + grp]; lo_n = rp[u]; hi_n = rp[u + 1]; du_n = (int)s.q[u]; }
             const uint8_t *trow = tab + du * W;
             const uint32_t cm = hi > lo ? (uint32_t)cmax[du] : 0u;      // 255 = nothing within the cutoff (never queued, but harmless)
             for (int e = lo + gl;; e += 8) {
+                uint32_t pk = 0xffffffffu;
+                if (e < hi) pk = edges[e];
                 const uint32_t code = pk >> 16;
                 const bool act = e < hi && cm != 255u && code <= cm;
                 if (act) {
@@ -107,10 +103,8 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
                     }
                 }
                 if (!__any_sync(GE_FULL, act && gl == 7)) break;        // no row filled its whole pass: every prefix is exhausted
-                pk = (e + 8 < hi) ? edges[e + 8] : 0xffffffffu;         // further passes of long prefixes load in place
             }
-            lo = lo_n; hi = hi_n; du = du_n; pk = pk_n;
-            lo_n = lo_nn; hi_n = hi_nn; du_n = du_nn;
+            lo = lo_n; hi = hi_n; du = du_n;
         }
         __syncwarp();
         ncur = *s.cnt;

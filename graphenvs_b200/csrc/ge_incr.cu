@@ -135,8 +135,10 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     int a;
     if (SAMPLED) {
         const uint32_t *mbits = d.mask_bits + (size_t)b * d.AW;
+        // small masks (<= 4 words per lane, e.g. config 3's 32 words): the whole mask in registers, one memory round
+        // (cfg3: 20.5 -> 18.8 us per step).  Larger masks keep the walk: 16 words per lane spill at this kernel's 32-register
+        // budget and measured slower at config 5 (162 vs 155 us).
         if (d.AW <= 4 * G) a = group_sample_regs<G, 4>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
-        else if (d.AW <= 16 * G) a = group_sample_regs<G, 16>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         else a = group_sample<G>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         if (lane == 0) actions[b] = a;
     } else {
