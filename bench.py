@@ -69,7 +69,9 @@ def layout_bytes_per_step(env):
                                          or (k == "MaxIndependentSet-v0" and N > 64))
     if incremental:
         has_bytes = False                                  # round 2: the incremental kernels keep only the packed mask current
-        sample = d.AW * 4                                  # the sampler walks the packed mask
+        sample = d.AW * 4                                  # the sampler walks the packed mask ...
+        if env.t.get("mask_cnt") is not None:              # ... or finds the chunk from 16 counts and reads that chunk (+ count updates)
+            sample = 32 + ((d.AW + 15) // 16) * 4 + 64
         if k == "MaxIndependentSet-v0":
             return float(fixed + sample + 2 * 8 + 4 + 32 + (1 if has_bytes else 0))
         upd = 2 * deg * (8 + (1 if has_bytes else 0))      # ~deg bits set + ~deg bits cleared (word r/w + byte)

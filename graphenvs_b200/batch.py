@@ -80,6 +80,8 @@ class BatchedGraphEnv:
                 T["esrc"] = z((B, d.MP), torch.int32)
             if env_id == "MulticastRouting-v0" and par >= 3:
                 T["bestkey"] = z((B, N), torch.int64)
+            if (env_id == "SteinerTree-v0" or (env_id == "MulticastRouting-v0" and par >= 2)) and d.AW > 64 and d.NW > 8:
+                T["mask_cnt"] = z((B, 8), torch.int32)                 # chunk popcounts of the packed mask for the in-kernel sampler
         if env_id == "DistributionCenter-v0":
             T["wmin"] = z((B,), torch.float64)
         T["src"] = z((B,), torch.int32)
@@ -145,7 +147,7 @@ class BatchedGraphEnv:
     def _sync_desc(self):
         for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "dc_edges", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "in_range_t", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
-                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask0_bits", "acc", "traj"):
+                     "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_cnt", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
             setattr(self.desc, name, t.data_ptr() if t is not None else None)
 

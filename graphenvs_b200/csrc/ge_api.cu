@@ -901,7 +901,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     ADV(src, 1); ADV(dest, 1); ADV(target_bits, d->NW); ADV(node_cost, d->N); ADV(node_xy, 2 * d->N); ADV(max_dist32, 1);
     ADV(targets, d->n_targets); ADV(in_range, (size_t)d->n_targets * d->NW); ADV(in_range_t, 4 * (size_t)d->N); ADV(heuristic, 1); ADV(heuristic_alt, 1); ADV(features, 5 * d->N);
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
-    ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
+    ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_cnt, 8); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
     ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);
 #undef ADV
     return GE_OK;   // dfa is shared by the whole batch; acc keeps the parent's component stride

@@ -39,11 +39,22 @@ constexpr u64 KEY_NONE = ~0ull;
 // store per changed edge, each a 32-byte sector read-modify-write in HBM: 2.3 KB of the 4.7 KB a Multicast step moved
 // (profiles/r01_final_step_kernel_cfg5_multicast.md, 2.55x the useful bytes).  The byte view (torch.bool for a policy)
 // is expanded on demand by ge_mask_bytes (ge_api.cu) in one coalesced pass.
+// Large masks additionally keep 16 CHUNK COUNTS (ge_batch.mask_cnt: popcount of every 1/16th of the mask, 16-bit counters,
+// one 32-byte sector per env): the in-kernel sampler then finds the chunk that holds the r-th valid action from that one
+// sector and reads just that chunk, two memory rounds and ~100 bytes instead of walking up to 1 KB of mask through
+// dependent loads (the walk was ~30 % of the instructions and 18 % of the stall samples of the Multicast step at config 5).
+__device__ __forceinline__ int mask_chunk_words(const ge_batch &d) { return (d.AW + 15) >> 4; }
+__device__ __forceinline__ void mask_count(const ge_batch &d, int b, int e, int delta) {
+    const int chunk = (e >> 5) / mask_chunk_words(d);
+    atomicAdd(&d.mask_cnt[(size_t)b * 8 + (chunk >> 1)], (uint32_t)delta << (16 * (chunk & 1)));   // counters never underflow: only set bits are cleared
+}
 __device__ __forceinline__ void mask_set(const ge_batch &d, int b, int e) {
     atomicOr(&d.mask_bits[(size_t)b * d.AW + (e >> 5)], 1u << (e & 31));
+    if (d.mask_cnt) mask_count(d, b, e, 1);
 }
 __device__ __forceinline__ void mask_clear(const ge_batch &d, int b, int e) {
     atomicAnd(&d.mask_bits[(size_t)b * d.AW + (e >> 5)], ~(1u << (e & 31)));
+    if (d.mask_cnt) mask_count(d, b, e, -1);
 }
 
 // Group-wide zero fill of an env's packed mask.
@@ -51,6 +62,51 @@ template <int G>
 __device__ __forceinline__ void mask_zero(const ge_batch &d, int b, int lane) {
     uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
     for (int w = lane; w < d.AW; w += G) mb[w] = 0;
+    if (d.mask_cnt && lane < 8) d.mask_cnt[(size_t)b * 8 + lane] = 0;
+}
+
+// r-th valid action through the chunk counts (same draw as group_sample: r-th set bit of the packed mask).
+template <int G>
+__device__ __forceinline__ int group_sample_chunks(const Grp<G> &g, const ge_batch &d, int b, uint64_t seed, uint32_t env, uint32_t t, int total) {
+    if (total <= 0) return -1;
+    const uint32_t r = (uint32_t)(((uint64_t)mix32(seed, env, t) * (uint64_t)total) >> 32);
+    const int CW = mask_chunk_words(d);
+    // stage 1: lanes 0..15 hold one chunk count each
+    int cnt = 0;
+    if (g.gl < 16) cnt = (int)((d.mask_cnt[(size_t)b * 8 + (g.gl >> 1)] >> (16 * (g.gl & 1))) & 0xffffu);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        const int x = __shfl_up_sync(g.mask, inc, o, G);
+        if (g.gl >= o) inc += x;
+    }
+    const unsigned hit = g.ballot((int)r < inc);
+    if (!hit) return -1;
+    const int chunk = __ffs(hit) - 1;
+    int rr = (int)r - (g.shfl(inc, chunk) - g.shfl(cnt, chunk));
+    // stage 2: the chunk's CW words, G at a time
+    const uint32_t *mb = d.mask_bits + (size_t)b * d.AW;
+    for (int w0 = chunk * CW; w0 < (chunk + 1) * CW; w0 += G) {
+        const int w = w0 + g.gl;
+        const uint32_t word = (w < d.AW && w < (chunk + 1) * CW) ? mb[w] : 0u;
+        const int c = __popc(word);
+        int in2 = c;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const int x = __shfl_up_sync(g.mask, in2, o, G);
+            if (g.gl >= o) in2 += x;
+        }
+        const int tot = g.shfl(in2, G - 1);
+        if (rr < tot) {
+            const unsigned h2 = g.ballot(rr < in2);
+            const int sl = __ffs(h2) - 1;
+            int pos = (g.gl == sl) ? nth_set_bit(word, rr - (in2 - c)) : 0;
+            pos = g.shfl(pos, sl);
+            return ((w0 + sl) << 5) + pos;
+        }
+        rr -= tot;
+    }
+    return -1;
 }
 
 // State init + first mask (tail of reset()) for the tree-growing kinds.  Returns nothing; all lanes.
@@ -139,6 +195,7 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
         // (cfg3: 20.5 -> 18.8 us per step).  Larger masks keep the walk: 16 words per lane spill at this kernel's 32-register
         // budget and measured slower at config 5 (162 vs 155 us).
         if (d.AW <= 4 * G) a = group_sample_regs<G, 4>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
+        else if (d.mask_cnt && G >= 16) a = group_sample_chunks<G>(g, d, b, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         else a = group_sample<G>(g, mbits, d.AW, seed, (uint32_t)(d.env_id0 + b), t + nsteps, c.y);
         if (lane == 0) actions[b] = a;
     } else {

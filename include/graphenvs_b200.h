@@ -158,6 +158,8 @@ typedef struct ge_batch {
                                               tree / nodes taken, popcount of the mask, constraints satisfied */
     uint8_t *done;                /* [B] */
     uint32_t *mask_bits;          /* [B, AW]  current valid-action mask, packed */
+    uint32_t *mask_cnt;           /* [B, 8]   incremental-mask kernels with large masks: popcounts of the 16 chunks of ceil(AW/16) words
+                                              of the packed mask, 16 bits each (state, maintained with the mask), or NULL */
     uint8_t *mask_bytes;          /* [B, AP]  same mask as bytes (torch.bool view) or NULL.  Kept current by the kernels that
                                               rewrite the whole mask; the INCREMENTAL-mask kernels (SteinerTree, Multicast p >= 2,
                                               MaxIndependentSet N > 64: ge_mask_bytes_current() == 0) update only the packed mask and

@@ -20,7 +20,7 @@ CFG = [
     ("DistributionCenter-v0", 12, 24, {"parenting": 2}), ("PerishableProductDelivery-v0", 12, 24, {"n_products": 3, "parenting": 1}),
     ("ShortestPath-v0", 70, 160, {}), ("TSP-v0", 70, 200, {"parenting": 2}), ("MaxIndependentSet-v0", 70, 160, {}),
 ]
-STATE = ("node_bits", "node_bits2", "edge_bits", "dist32", "bestkey", "head", "cost", "counters", "done", "mask_bits", "mask_bytes")
+STATE = ("node_bits", "node_bits2", "edge_bits", "dist32", "bestkey", "head", "cost", "counters", "done", "mask_bits", "mask_bytes", "mask_cnt")
 
 
 @pytest.mark.parametrize("force_warp", [False, True], ids=["fast", "general"])
