@@ -145,6 +145,31 @@ __global__ void __launch_bounds__(512, 1) features_cta_kernel(ge_batch d, int NW
         __syncwarp();
         int level = 0, reached = 1;
         long long totsp = 0;
+        {   // level 1 is N(s) itself, every node with exactly one shortest path: no scan of the ~N unvisited nodes for it
+            const uint32_t *rs = mat + (size_t)s * NWP;
+            uint32_t newbits = 0;
+            for (int j = 0; j < NW; ++j)
+                if ((rs[j] >> lane) & 1u) {
+                    const int v = lane + (j << 5);
+                    sigma[v] = 1.0; delta[v] = 0.0; D[v] = 1;
+                    newbits |= 1u << j;
+                }
+            const uint32_t myword = lane < NW ? rs[lane] : 0u;
+            const uint32_t nz = __ballot_sync(GE_FULL, myword != 0u);
+            if (nz) {
+                unv &= ~newbits;
+                if (lane < NW) lv[lane] = myword;
+                quads = 0;
+#pragma unroll
+                for (int qi = 0; qi < 8; ++qi)
+                    if ((nz >> (4 * qi)) & 0xfu) quads |= 1u << qi;
+                const int cnt = __reduce_add_sync(GE_FULL, __popc(myword));
+                level = 1;
+                reached += cnt;
+                totsp += cnt;
+            }
+            __syncwarp();
+        }
         while (reached < N) {  // forward sweep (_single_source_shortest_path_basic), pull form
             ++level;
             uint32_t newbits = 0, rem = unv;
