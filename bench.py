@@ -402,6 +402,27 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
     envs_all = D.reduce([B], "sum")[0]
     value = envs_all * K / (total_ms_max * 1e-3)
 
+    # ---- what an event pair around an (almost) empty kernel measures in the same kind of graph: the share of every timed step
+    #      that is launch + event overhead, not kernel (headline only)
+    floor_ms = None
+    if sampler is not None:
+        try:
+            tiny = torch.zeros(32, device=dev)
+            fe = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(2)] for _ in range(32)]
+            fg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(fg):
+                for i in range(32):
+                    flush()
+                    fe[i][0].record()
+                    tiny.add_(1.0)
+                    fe[i][1].record()
+            for _ in range(2):
+                fg.replay()
+            torch.cuda.synchronize()
+            floor_ms = float(np.mean([a.elapsed_time(b) for a, b in fe]))
+        except Exception:
+            floor_ms = None
+
     # ---- end to end through the C ABI with host buffers (ge_step_host); the policy between calls is untimed
     d = env.desc
     h_blk, h_rew, h_flg, h_cost, h_bits = env.host_io()
@@ -505,6 +526,9 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "e2e_obs": e2e_obs,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
+                     "event_pair_floor_ms": floor_ms,
+                     "event_pair_floor_note": "the same event pair around a 32-element add kernel in the same kind of graph: launch + event "
+                                              "overhead contained in kernel_ms (achieved / frac are NOT corrected for it)",
                      "bytes_per_env_step": lib_bytes,
                      "bytes_model": "compulsory bytes of this engine's layout and algorithm per env-step (bench.py:layout_bytes_per_step)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
