@@ -521,8 +521,13 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
                 "value_with_device_policy_between_calls": e2e_dev_val,
-                "timed": ("sum of ge_step_host calls: pinned H2D actions, step kernel, D2H of reward/flags/solution_cost/packed mask, "
-                          "completion wait (%s%s); policy between calls untimed" % (args.e2e, ", %d slices" % args.e2e_chunks if args.e2e == "pipelined" else ""))},
+                "timed": ("sum of the host-step calls on pinned host buffers, " + (
+                    "ge_step_host_pipelined: %d slices on one CUDA graph; the step kernels read the int32 actions straight from the pinned "
+                    "host buffer over PCIe (no staging copy), a write-back kernel streams each slice's reward / flags / solution_cost / packed "
+                    "mask into the pinned host arrays while the next slice steps; completion polled" % args.e2e_chunks
+                    if args.e2e == "pipelined" else
+                    "ge_step_host: H2D copy of the actions, step kernel, one D2H copy of reward / flags / solution_cost / packed mask, stream sync")
+                    + "; policy between calls untimed")},
         "e2e_obs": e2e_obs,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
