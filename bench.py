@@ -317,6 +317,82 @@ class L2Flush:
             self.torch.sum(self.rd, dim=(0,), out=self.sink)
 
 
+L2_BYTES = 126e6
+# sub-batch chains per step in the streaming protocol (graphenvs_b200.batch.SliceStreams); measured sweet spots
+STREAM_CHUNKS = {"cfg2_longest_path": 8, "cfg1_shortest_path": 8, "perishable": 4, "cfg3_mst": 2, "densest": 2,
+                 "cfg5_multicast": 2, "cfg5_distcenter": 2}   # (profiles/r02_stream_sweep.jsonl)
+
+
+def measure_streaming(D, wl, B, K, W, env, env0, args, per_launch_bytes):
+    """Streaming protocol: EXACTLY K steps inside ONE timed region (one CUDA event pair, barrier + synchronize on both sides),
+    no flush kernels in it.  The steps rotate over R independent resident batches of B envs whose per-step traffic adds up to
+    > 3x L2 (inputs larger than L2: every step finds its batch cold); a workload whose single batch already moves more than
+    that per step uses R = 1.  One step of a batch = C sub-batch launches on C free-running stream chains (envs are
+    independent: step t+1 of an env only has to follow step t of the same env), launched with GE_FLAG_PDL.
+    Returns None when the R batches do not fit in memory (then only the isolated protocol is reported)."""
+    import torch
+    from graphenvs_b200 import BatchedGraphEnv
+    from graphenvs_b200.batch import SliceStreams
+    env_id, N, E, kw, _, _, _ = WORKLOADS[wl]
+    dev = D.dev
+    R = int(max(1, -(-3 * L2_BYTES // max(per_launch_bytes, 1.0))))
+    free, _total = torch.cuda.mem_get_info(dev)
+    if R > 1 and (R > 48 or (R - 1) * env.memory_bytes() * 1.3 > 0.8 * free):
+        return None
+    C_ = args.stream_chunks or STREAM_CHUNKS.get(wl, 1)
+    envs = [env]
+    for r in range(1, R):
+        e = BatchedGraphEnv(env_id, B, N, E, device=dev, auto_reset=True, env_id0=env0 + r * B * D.world, **kw)
+        e.generate(seed=SEED)
+        e.release_w64()
+        e.reset()
+        e.enable_env_clock()
+        envs.append(e)
+    for e in envs:
+        e.enable_pdl(not args.no_pdl)
+    streams, sl = None, None
+    if C_ > 1:
+        streams = [torch.cuda.Stream(device=dev) for _ in range(C_)]
+        sl = [SliceStreams(e, C_, streams=streams) for e in envs]
+    for _ in range(max(W, 3)):
+        for e in envs:
+            e.step_sampled(SEED, 0)
+    torch.cuda.synchronize()
+    G = max(g for g in range(1, min(K, 1024) + 1) if K % g == 0)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        if sl:
+            sl[0].fork()
+        for i in range(G):
+            if sl:
+                sl[i % R].step_sampled(SEED, 0)
+            else:
+                envs[i % R].step_sampled(SEED, 0)
+        if sl:
+            sl[0].join()
+    graph.replay()   # untimed (graph upload)
+    D.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    a.record()
+    for _ in range(K // G):
+        graph.replay()
+    b.record()
+    D.barrier()
+    w1 = time.time()
+    ms = a.elapsed_time(b)
+    total_ms_max = D.reduce([ms], "max")[0]
+    for e in envs:
+        e.enable_pdl(False)
+    n_launch = K * (len(sl[0].bounds) if sl else 1)
+    del graph, sl, envs
+    torch.cuda.empty_cache()
+    return {"total_ms": total_ms_max, "ms_per_step": total_ms_max / K, "steps": K, "replicas": R, "chunks": C_, "pdl": not args.no_pdl,
+            "gpu_launches": n_launch, "wall": (w0, w1), "rotation_bytes": per_launch_bytes * R,
+            "launch": "CUDA graph of %d steps replayed %d times, ONE event pair around all %d steps; step i runs on batch i %% %d; "
+                      "each step = %d sub-batch launch(es) on %d stream chain(s)%s" % (G, K // G, K, R, C_, C_, ", programmatic dependent launch" if not args.no_pdl else "")}
+
+
 def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_note=None, sampler=None, seed_env0=None):
     """One workload on this rank's B envs: device-timed env-steps/s (value), the end-to-end C-ABI number (e2e), the
     roofline of the step kernel, reset-time costs.  Every rank calls it with the same arguments (barriers inside)."""
@@ -395,12 +471,32 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         kern_ms += [e[0 if fused else 1].elapsed_time(e[2]) for e in events]
     D.barrier()
     w1 = time.time()
-    clocks = sampler.stop(w0, w1) if sampler is not None else None
     step_ms, kern_ms = np.array(step_ms), np.array(kern_ms)
     assert step_ms.size == K
     total_ms_max, kern_ms_mean = D.reduce([float(step_ms.sum()), float(kern_ms.mean())], "max")
     envs_all = D.reduce([B], "sum")[0]
-    value = envs_all * K / (total_ms_max * 1e-3)
+    iso_value = envs_all * K / (total_ms_max * 1e-3)
+    isolated = {"value": iso_value, "unit": UNIT, "ms_per_step": total_ms_max / K, "steps": K, "kernel_ms": kern_ms_mean, "launch": launch_mode,
+                "gpu_launches": (1 if fused else 2) * K, "wall_ms_per_step_incl_flush": 1e3 * (w1 - w0) / K,
+                "l2": "256 MiB flush %s before every timed step; per-step CUDA event pairs exclude it" % args.flush}
+    graph = replay = None                                      # release the isolated-protocol graph
+    traffic, traffic_src = None, None
+    try:   # measured DRAM bytes per launch of the step kernel (ncu), when this workload/batch was profiled
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
+        if tr and tr.get("envs") == B:
+            traffic = tr["bytes_per_launch"]
+            traffic_src = "ncu --set full capture of this kernel at this batch (%s); carried from profiles/traffic.json, not measured in this run" % tr.get("source", "profiles/")
+    except Exception:
+        tr = None
+    per_launch = traffic if traffic else (tr["bytes_per_launch"] * B / tr["envs"] if tr else lib_bytes * B)
+    stream = None
+    if fused and not args.no_streaming:
+        stream = measure_streaming(D, wl, B, K, W, env, env0, args, per_launch)
+    clocks = sampler.stop(w0, stream["wall"][1] if stream else w1) if sampler is not None else None
+    if stream:
+        value, ms_per_step, kern_ms_mean, launch_mode, n_launches = envs_all * K / (stream["total_ms"] * 1e-3), stream["ms_per_step"], stream["ms_per_step"], stream["launch"], stream["gpu_launches"]
+    else:
+        value, ms_per_step, n_launches = iso_value, total_ms_max / K, isolated["gpu_launches"]
 
     # ---- what an event pair around an (almost) empty kernel measures in the same kind of graph: the share of every timed step
     #      that is launch + event overhead, not kernel (headline only)
@@ -504,20 +600,16 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, traffic_src = None, None
-    try:   # measured DRAM bytes per launch of the step kernel (ncu), when this workload/batch was profiled
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
-        if tr and tr.get("envs") == B:
-            traffic = tr["bytes_per_launch"]
-            traffic_src = "ncu --set full capture of this kernel at this batch (%s); carried from profiles/traffic.json, not measured in this run" % tr.get("source", "profiles/")
-    except Exception:
-        pass
     achieved = lib_bytes * B / (kern_ms_mean * 1e-3) / 1e9
     res = {
         "name": wl, "workload": desc if envs_total_note is None else envs_total_note,
-        "value": value, "unit": UNIT, "ms_per_step": total_ms_max / K, "steps": K, "envs_per_gpu": B, "envs_total": int(envs_all),
+        "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": K, "envs_per_gpu": B, "envs_total": int(envs_all),
+        "protocol": ("streaming: K steps in one timed region rotating over %d resident batches (%.0f MB touched per rotation > L2), no flush" %
+                     (stream["replicas"], stream["rotation_bytes"] / 1e6)) if stream else "isolated: L2 flush + one event pair per step",
+        "streaming": {k: stream[k] for k in ("replicas", "chunks", "pdl", "rotation_bytes")} if stream else None,
+        "isolated": isolated,
         "launch": launch_mode, "clocks": clocks,
-        "gpu_launches": (1 if fused else 2) * K,
+        "gpu_launches": n_launches,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
                 "value_with_device_policy_between_calls": e2e_dev_val,
@@ -531,9 +623,12 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "e2e_obs": e2e_obs,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
+                     "kernel_ms_what": ("timed region / steps under the streaming protocol (sub-batch launches overlap, so this is the time one "
+                                        "full-batch step takes in steady state)" if stream else "mean of the per-step event pairs (isolated protocol)"),
+                     "frac_isolated": lib_bytes * B / (isolated["kernel_ms"] * 1e-3) / 1e9 / peak,
                      "event_pair_floor_ms": floor_ms,
-                     "event_pair_floor_note": "the same event pair around a 32-element add kernel in the same kind of graph: launch + event "
-                                              "overhead contained in kernel_ms (achieved / frac are NOT corrected for it)",
+                     "event_pair_floor_note": "isolated protocol only: the same event pair around a 32-element add kernel in the same kind of "
+                                              "graph = launch + event overhead contained in every isolated kernel_ms (frac_isolated is NOT corrected for it)",
                      "bytes_per_env_step": lib_bytes,
                      "bytes_model": "compulsory bytes of this engine's layout and algorithm per env-step (bench.py:layout_bytes_per_step)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -542,7 +637,6 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
                      "frac_if_full_recompute_note": "SURVEY 8(d) bytes of a from-scratch recompute over CSR; NOT this kernel's traffic "
                                                     "(incremental masks / pruned searches move fewer bytes), may exceed 1"},
         "reset": reset_block,
-        "wall_ms_per_step_incl_flush": 1e3 * (w1 - w0) / K,
         "episodes": float(stats[0]), "solved": float(stats[1]),
         "memory_gb_per_gpu": mem / 1e9,
     }
@@ -551,11 +645,12 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
 
 def compact(res):
     """Entry of the `workloads` array: the figures VERDICT r01 asked the driver-run line to carry per workload."""
-    keep = ("name", "workload", "value", "unit", "ms_per_step", "steps", "envs_per_gpu", "e2e", "e2e_obs", "reset", "cpu_baseline",
-            "cpu_reference_python", "episodes")
+    keep = ("name", "workload", "value", "unit", "ms_per_step", "steps", "envs_per_gpu", "protocol", "streaming", "gpu_launches", "e2e", "e2e_obs",
+            "reset", "cpu_baseline", "cpu_reference_python", "episodes")
     out = {k: res.get(k) for k in keep if k in res}
     r = res["roofline"]
-    out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_ms", "bytes_per_env_step")}
+    out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_isolated", "traffic", "kernel", "kernel_ms", "bytes_per_env_step")}
+    out["isolated"] = {k: res["isolated"][k] for k in ("value", "ms_per_step", "kernel_ms")}
     out["e2e"] = {k: res["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "policy")}
     return out
 
@@ -708,14 +803,17 @@ def run_ours(args):
                        "instances": "device generator ge_generate (connected G(n,m), reference weight law), seed %d" % SEED,
                        "policy": "uniform valid action, device counter RNG, inside the timed step (%s)" %
                                  ("drawn in the step kernel, ge_step_sampled" if args.mode == "fused" else "ge_sample_actions + ge_step"),
-                       "auto_reset": True, "l2": "256 MiB flush %s between timed steps (per-step CUDA events exclude it)" % args.flush,
+                       "auto_reset": True,
+                       "l2": ("inputs larger than L2: the timed steps rotate over %d independent resident batches of %d envs (%.0f MB touched per "
+                              "rotation vs 126 MB of L2), no flush inside the timed region" % (head["streaming"]["replicas"], B, head["streaming"]["rotation_bytes"] / 1e6))
+                             if head["streaming"] else "256 MiB flush %s between timed steps (per-step CUDA events exclude it)" % args.flush,
                        "launch": head["launch"], "byte_mask": True},
             "clocks": head["clocks"],
             "gpu_launches": head["gpu_launches"],
             "e2e": head["e2e"], "e2e_obs": head["e2e_obs"],
             "roofline": head["roofline"],
             "reset": head["reset"],
-            "wall_ms_per_step_incl_flush": head["wall_ms_per_step_incl_flush"],
+            "protocol": head["protocol"], "streaming": head["streaming"], "isolated": head["isolated"],
             "episodes": head["episodes"], "solved": head["solved"], "memory_gb_per_gpu": head["memory_gb_per_gpu"],
             "cpu_reference_python": head["cpu_reference_python"],
             "workloads": workloads,
@@ -759,6 +857,9 @@ def main():
     ap.add_argument("--e2e-device-policy", action="store_true",
                     help="headline e2e: draw the actions with the device sampler between calls (untimed) instead of the host numpy policy")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the pipelined end-to-end step")
+    ap.add_argument("--no-streaming", action="store_true", help="isolated protocol only (L2 flush + one event pair per step)")
+    ap.add_argument("--no-pdl", action="store_true", help="streaming protocol without programmatic dependent launch")
+    ap.add_argument("--stream-chunks", type=int, default=0, help="sub-batch chains per step in the streaming protocol (0 = per-workload table)")
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: ge_step_sampled (one launch per step); split: ge_sample_actions + ge_step")
     args = ap.parse_args()

@@ -159,6 +159,12 @@ class BatchedGraphEnv:
             self.desc.env_steps = self.env_steps.data_ptr()
         return self.env_steps
 
+    def enable_pdl(self, on=True):
+        """GE_FLAG_PDL (include/graphenvs_b200.h): step launches may start under the tail of the previous launch of the stream
+        and prefetch static instance data; valid while the preceding work in the stream is another step (not generate() /
+        finalize_graphs() / an InstancePool refill, which rewrite static arrays)."""
+        self.desc.flags = (self.desc.flags | 16) if on else (self.desc.flags & ~16)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -574,3 +580,49 @@ class BatchedGraphEnv:
     def load_state_dict(self, sd):
         for k, v in sd.items():
             self.t[k].copy_(v)
+
+
+class SliceStreams:
+    """C sub-batches of ONE resident batch, each advanced on its own CUDA stream.
+
+    Envs are independent, so step t+1 of an env only has to follow step t of the SAME env: slice c's launches form a chain
+    on stream c, and the chains are not ordered against each other.  A launch over a whole small-graph batch is one wave
+    of the machine that alternates between an all-memory phase (state + adjacency tiles in) and an all-compute phase (the
+    mask searches); C free-running chains de-phase, so one slice's searches run under another slice's loads.
+
+        ss = SliceStreams(env, 4)
+        ss.fork()                       # the slice streams wait for what is on the current stream
+        for t in range(T): ss.step_sampled(seed, t)
+        ss.join()                       # the current stream waits for every slice
+    Works under CUDA-graph capture (fork / join become the graph's fork / join edges)."""
+
+    def __init__(self, env, chunks, streams=None):
+        self.env = env                                          # (descriptor is read NOW: enable_env_clock() / enable_pdl() first)
+        B, C_ = env.B, int(chunks)
+        per = ((B + C_ - 1) // C_ + 31) // 32 * 32             # slice starts are multiples of 32 envs (tiled adjacency)
+        self.bounds = [(lo, min(per, B - lo)) for lo in range(0, B, per)]
+        self.descs = [env.slice_desc(lo, n) for lo, n in self.bounds]
+        self.outs = [_native.StepOut(_ptr(env.reward[lo:]), _ptr(env.flags[lo:]), _ptr(env.solution_cost[lo:])) for lo, _ in self.bounds]
+        self.acts = [_ptr(env.actions_dev[lo:]) for lo, _ in self.bounds]
+        self.streams = streams if streams is not None else [torch.cuda.Stream(device=env.device) for _ in self.bounds]
+        assert len(self.streams) >= len(self.bounds)
+
+    def fork(self):
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def step_sampled(self, seed, t):
+        L = self.env.lib
+        for d, o, a, s in zip(self.descs, self.outs, self.acts, self.streams):
+            _native.check(L.ge_step_sampled(C.byref(d), int(seed), int(t), a, C.byref(o), C.c_void_p(s.cuda_stream)))
+
+    def step(self, actions):
+        L = self.env.lib
+        for (lo, _), d, o, s in zip(self.bounds, self.descs, self.outs, self.streams):
+            _native.check(L.ge_step(C.byref(d), _ptr(actions[lo:]), C.byref(o), C.c_void_p(s.cuda_stream)))

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(GE_WPB * 32, MINB) step_kernel(ge_batch d, int
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     Scr s = carve(smem + (size_t)warp * words_per_warp, d);
     EnvPtrs p = env_ptrs(d, b);
@@ -677,8 +679,7 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     const bool six = d->kind == GE_DISTRIBUTION_CENTER && d->wcode && d->dfa && !getenv("GE_DC_MINB4");
     auto kernel = sampled ? (six ? step_kernel<true, 6> : step_kernel<true, 4>) : (six ? step_kernel<false, 6> : step_kernel<false, 4>);
     if ((rc = set_smem(kernel, smem))) return rc;
-    kernel<<<blocks, GE_WPB * 32, smem, (cudaStream_t)stream>>>(*d, actions, *out, wpw, seed, t);
-    GE_CUDA_OK(cudaGetLastError());
+    GE_CUDA_OK(ge_launch_step(kernel, dim3(blocks), dim3(GE_WPB * 32), smem, (cudaStream_t)stream, *d, actions, *out, wpw, seed, t));
     return GE_OK;
 }
 
@@ -984,10 +985,12 @@ static int pipelined_copy_in(const ge_batch *d, int lo, int n, const int32_t *h_
     GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     return GE_OK;
 }
-static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
+static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s,
+                          uint32_t *h_mask_bits = nullptr) {
     ge_batch sl;
     int rc = ge_batch_slice(d, lo, n, &sl);
     if (rc) return rc;
+    if (h_mask_bits) sl.mask_mirror = h_mask_bits + (size_t)lo * d->AW;   // direct mode: the kernel stores the packed mask on both sides
     ge_step_out so = {out->reward + lo, out->flags + lo, out->solution_cost + lo};
     return ge_step(&sl, d_actions + lo, &so, (void *)s);
 }
@@ -1026,12 +1029,17 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
         // three-lane sequence for the following calls
         const bool zc = env_flag("GE_PIPE_ZC", &g_pipe_zc, true);
+        // direct mode (GE_PIPE_DIRECT=1, experiment): no write-back kernels -- the step kernels store reward / flags / solution_cost /
+        // packed mask straight into the pinned host arrays (coalesced 128-256 byte PCIe writes per warp)
+        static int g_pipe_direct = -1;
+        const bool direct = zc && env_flag("GE_PIPE_DIRECT", &g_pipe_direct) && ge_mask_mirror_supported(d) && h_solution_cost && h_mask_bits;
+        const ge_step_out host_out = {h_reward, h_flags, h_solution_cost};
         const int32_t *acts = zc ? h_actions : d_actions;
         for (int i = 0; i < chunks; ++i) {
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
             if (!zc && (rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
-            if ((rc = pipelined_step(d, lo, n, acts, out, st))) return rc;
-            if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
+            if ((rc = pipelined_step(d, lo, n, acts, direct ? &host_out : out, st, direct ? h_mask_bits : nullptr))) return rc;
+            if (!direct && (rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lock(g_hsg_mu);
@@ -1061,7 +1069,8 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
                     rc2 = pipelined_copy_in(d, lo, n, h_actions, d_actions, s_in);
                     ok = ok && cudaEventRecord(g_in[i], s_in) == cudaSuccess && cudaStreamWaitEvent(st, g_in[i], 0) == cudaSuccess;
                 }
-                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, out, st);
+                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, direct ? &host_out : out, st, direct ? h_mask_bits : nullptr);
+                if (direct) continue;
                 ok = ok && cudaEventRecord(g_stepped[i], st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_stepped[i], 0) == cudaSuccess;
                 if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s_out);
             }

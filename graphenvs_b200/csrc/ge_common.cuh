@@ -28,9 +28,35 @@ struct GeNvtxRange {
 #define GE_FULL 0xffffffffu
 #define GE_WPB 8  // warps (= environments) per thread block
 
+// Step-kernel launch.  With GE_FLAG_PDL in the descriptor (or GE_PDL=1 in the environment, for A/B runs) the launch carries the
+// programmatic-stream-serialization attribute: the kernel may become resident while the previous launch of the stream is
+// still running; its pdl_wait() (below) is then what orders it behind that launch (include/graphenvs_b200.h: GE_FLAG_PDL).
+#include <cstdlib>
+inline bool ge_pdl_env() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("GE_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t ge_launch_step(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const ge_batch &d, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ((d.flags & GE_FLAG_PDL) || ge_pdl_env()) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, d, args...);
+    return e == cudaSuccess ? cudaGetLastError() : e;
+}
+
 namespace ge {
 
 typedef unsigned long long u64;
+
+// griddepcontrol (sm_90+): no-ops when the kernel was not launched as a programmatic dependent.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Per-warp shared-memory scratch.
 struct Scr {

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): the automaton (static) is staged before pdl_wait()
     const int S = d.dfa[0], W = d.dfa[1];
     {   // automaton tables: one copy per block
         uint8_t *dst = reinterpret_cast<uint8_t *>(smem);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
         for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = d.dfa[i];
     }
     __syncthreads();
+    pdl_wait();
     if (b >= d.B) return;
     const uint8_t *tab = reinterpret_cast<const uint8_t *>(smem) + 2, *expand = tab + S * W, *cmax = expand + S;
     DcScr s = dc_carve(smem + dfa_words + (size_t)warp * warp_words, d);
@@ -432,7 +434,7 @@ int ge_dc_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool
     auto kernel = sampled ? dc_step_kernel<true> : dc_step_kernel<false>;
     int rc = ge_grant_smem((const void *)kernel, smem);
     if (rc) return rc;
-    kernel<<<(d->B + GE_WPB - 1) / GE_WPB, GE_WPB * 32, smem, st>>>(*d, actions, *out, seed, t, dfa_words, ww);
+    ge_launch_step(kernel, dim3((d->B + GE_WPB - 1) / GE_WPB), dim3(GE_WPB * 32), smem, st, *d, actions, *out, seed, t, dfa_words, ww);
     return dc_launched("dc_step_kernel");
 }
 

@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(256, 8) group_step_kernel(ge_batch d, int32_t 
     const Grp<G> g;
     const int lane = g.gl;
     const int b = blockIdx.x * (256 / G) + (int)threadIdx.x / G;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     const int N = d.N, NW = d.NW, kind = d.kind;
     const bool W = lane < NW;
@@ -382,7 +384,7 @@ int ge_group_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, b
     auto kernel = G == 8 ? (sampled ? group_step_kernel<true, 8> : group_step_kernel<false, 8>)
                 : G == 16 ? (sampled ? group_step_kernel<true, 16> : group_step_kernel<false, 16>)
                           : (sampled ? group_step_kernel<true, 32> : group_step_kernel<false, 32>);
-    kernel<<<blocks, 256, 0, st>>>(*d, actions, *out, seed, t);
+    ge_launch_step(kernel, dim3(blocks), dim3(256), 0, st, *d, actions, *out, seed, t);
     return group_launched("group_step_kernel");
 }
 

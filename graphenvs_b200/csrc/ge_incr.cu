@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(GE_WPB * 32, GE_INCR_MINB) incr_tree_step_kern
     const Grp<G> g;
     const int lane = g.gl;  // lane inside the env's group
     const int b = blockIdx.x * (GE_WPB * 32 / G) + (int)threadIdx.x / G;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     const bool mc = d.kind == GE_MULTICAST_ROUTING;
     const int N = d.N;
@@ -334,6 +336,8 @@ template <bool SAMPLED>
 __global__ void __launch_bounds__(256) incr_mis_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out, uint64_t seed,
                                                           uint32_t t) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     const int N = d.N;
     const uint32_t nsteps = d.env_steps ? d.env_steps[b] : 0u;
@@ -411,8 +415,7 @@ static int launched(const char *what) {
 
 int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bool sampled, uint64_t seed, uint32_t t, cudaStream_t st) {
     if (d->kind == GE_MAX_INDEPENDENT_SET) {
-        if (sampled) incr_mis_step_kernel<true><<<(d->B + 255) / 256, 256, 0, st>>>(*d, actions, *out, seed, t);
-        else incr_mis_step_kernel<false><<<(d->B + 255) / 256, 256, 0, st>>>(*d, actions, *out, seed, t);
+        ge_launch_step(sampled ? incr_mis_step_kernel<true> : incr_mis_step_kernel<false>, dim3((d->B + 255) / 256), dim3(256), 0, st, *d, actions, *out, seed, t);
         return launched("incr_mis_step_kernel");
     }
     // lanes per env: wide enough to hold the node bitsets in registers (NW <= G) and a typical row in one pass
@@ -425,7 +428,7 @@ int ge_incr_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bo
     auto kernel = G == 8 ? (sampled ? incr_tree_step_kernel<true, 8> : incr_tree_step_kernel<false, 8>)
                 : G == 16 ? (sampled ? incr_tree_step_kernel<true, 16> : incr_tree_step_kernel<false, 16>)
                           : (sampled ? incr_tree_step_kernel<true, 32> : incr_tree_step_kernel<false, 32>);
-    kernel<<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
+    ge_launch_step(kernel, dim3(blocks), dim3(GE_WPB * 32), 0, st, *d, actions, *out, seed, t);
     return launched("incr_tree_step_kernel");
 }
 

@@ -268,10 +268,15 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const int b0 = blockIdx.x * blockDim.x, b = b0 + threadIdx.x;
+    // Programmatic dependent launch (ge_common.cuh:pdl_*; no-ops on a plain launch): the next launch in the stream may
+    // become resident now, and everything up to pdl_wait() touches only STATIC instance data (the adjacency tiles), so
+    // it runs under the tail of the previous launch.
+    pdl_launch_dependents();
     Rows<STAGED> R = stage_rows<STAGED>(d, b0, smem, &bar);
     const bool live = b < d.B;
     const int N = d.N, kind = d.kind;
     const u64 full = N == 64 ? ~0ull : ((1ull << N) - 1ull);
+    pdl_wait();
     // scalar state (coalesced SoA streams) while the bulk copy is in flight
     LState s;
     int a = -1, dest = 0, src = 0;
@@ -474,7 +479,7 @@ static int lane_threads(const ge_batch *d) {
         if (forced != 32 && forced != 64 && forced != 128) forced = 0;
     }
     if (forced) return forced;
-    return 64;
+    return 32;   // one tile per block: 9.96 vs 10.17 us per cfg2 step under the streaming protocol; no difference when a step runs alone
 }
 static size_t lane_smem(const ge_batch *d, int T) { return lane_stages(*d) ? (size_t)T * d->N * d->NW * 4 : 0; }
 
@@ -491,8 +496,7 @@ int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bo
                                   : (sampled ? lane_step_kernel<false, true> : lane_step_kernel<false, false>);
     int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
-    kernel<<<(d->B + T - 1) / T, T, smem, st>>>(*d, actions, *out, seed, t);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = ge_launch_step(kernel, dim3((d->B + T - 1) / T), dim3(T), smem, st, *d, actions, *out, seed, t);
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_step_kernel launch: %s", cudaGetErrorString(e));
 }
 

@@ -52,6 +52,8 @@ template <bool SAMPLED>
 __global__ void __launch_bounds__(GE_WPB * 32) ppd_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out, uint64_t seed, uint32_t t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * GE_WPB + warp;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     const int N = d.N, P = d.n_dests;
     const uint32_t *adj = d.adj_bits + (size_t)b * d.ADJS;
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__(GE_WPB * 32) ppd_step_kernel(ge_batch d, int32
 template <bool SAMPLED>
 __global__ void __launch_bounds__(128) ppd_lane_step_kernel(ge_batch d, int32_t *__restrict__ actions, ge_step_out out, uint64_t seed, uint32_t t) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();   // programmatic dependent launch (ge_common.cuh): no-ops on a plain launch
+    pdl_wait();
     if (b >= d.B) return;
     const int N = d.N, P = d.n_dests, NW = d.NW;
     const int32_t *tg = d.targets + (size_t)b * d.n_targets;
@@ -289,13 +293,11 @@ int ge_ppd_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, boo
     if (rc) return rc;
     if (ge_ppd_lane(d)) {
         const int T = 128, blocks = (d->B + T - 1) / T;
-        if (sampled) ppd_lane_step_kernel<true><<<blocks, T, 0, st>>>(*d, actions, *out, seed, t);
-        else ppd_lane_step_kernel<false><<<blocks, T, 0, st>>>(*d, actions, *out, seed, t);
+        ge_launch_step(sampled ? ppd_lane_step_kernel<true> : ppd_lane_step_kernel<false>, dim3(blocks), dim3(T), 0, st, *d, actions, *out, seed, t);
         return ppd_launched("ppd_lane_step_kernel");
     }
     const int blocks = (d->B + GE_WPB - 1) / GE_WPB;
-    if (sampled) ppd_step_kernel<true><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
-    else ppd_step_kernel<false><<<blocks, GE_WPB * 32, 0, st>>>(*d, actions, *out, seed, t);
+    ge_launch_step(sampled ? ppd_step_kernel<true> : ppd_step_kernel<false>, dim3(blocks), dim3(GE_WPB * 32), 0, st, *d, actions, *out, seed, t);
     return ppd_launched("ppd_step_kernel");
 }
 
