@@ -570,6 +570,9 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
     e2e_obs = None
     if args.e2e_obs and hasattr(env, "obs_nodes"):
         xbuf = torch.empty((B, N, env.F), dtype=torch.float32, device=dev)
+        fused_obs = args.e2e == "pipelined"
+        if fused_obs:     # ge_batch.obs_x: every slice's node columns are rewritten on the write-back lane of the SAME call
+            stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True, chunks=args.e2e_chunks, obs_x=xbuf)
         t_obs = 0.0
         Ko = max(3, min(Ke, 20))
         for k in range(2 + Ko):
@@ -579,14 +582,21 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
             torch.cuda.synchronize()
             c0 = time.perf_counter()
             stepper()
-            env.obs_nodes(out=xbuf)
-            torch.cuda.synchronize()
+            if not fused_obs:
+                env.obs_nodes(out=xbuf)
+                torch.cuda.synchronize()
             c1 = time.perf_counter()
             if k >= 2:
                 t_obs += c1 - c0
         t_obs_max = D.reduce([t_obs], "max")[0]
+        if fused_obs:     # the rewritten columns are those of the state after the step
+            ref_x = env.obs_nodes()
+            assert torch.equal(ref_x, xbuf), "obs_x written by the pipelined step differs from ge_obs_nodes"
+            env.desc.obs_x = None
         e2e_obs = {"value": envs_all * Ko / t_obs_max, "unit": UNIT, "steps": Ko, "obs_bytes_written_per_env": N * env.F * 4,
-                   "what": "ge_step_host (host actions in, results out) + ge_obs_nodes: x float32[B, N, F] rewritten on the device every step"}
+                   "what": ("ge_step_host_pipelined with ge_batch.obs_x set: host actions in, results out, and x float32[B, N, F] (the observation's "
+                            "node columns, utils.py:14-23) rewritten on the device slice by slice on the write-back lane of the same call")
+                           if fused_obs else "ge_step_host (host actions in, results out) + ge_obs_nodes: x float32[B, N, F] rewritten on the device every step"}
 
     from graphenvs_b200.sharding import reduce_stats
     stats = reduce_stats(env.stats().clone()).cpu().numpy()

@@ -469,12 +469,17 @@ class BatchedGraphEnv:
                                             _ptr(h_flags), _ptr(h_cost), None, _ptr(h_mask_bits), self._stream()))
 
     def host_stepper(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None, stream=None, pipelined=False,
-                     chunks=4):
+                     chunks=4, obs_x=None):
         """Zero-argument callable = step_host on FIXED pinned buffers, arguments marshalled once.  On a
         non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph.
         pipelined=True: ge_step_host_pipelined -- the batch is stepped in `chunks` slices on parallel graph branches,
         slice i's results cross PCIe while slice i+1 steps (needs a created stream; the byte mask is not returned)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        # obs_x: float32[B, N, F] on the device -- the pipelined step also rewrites the observation's node columns, slice by
+        # slice on its write-back lane (ge_batch.obs_x); None switches that off again
+        assert obs_x is None or (pipelined and obs_x.is_cuda and obs_x.dtype == torch.float32 and obs_x.is_contiguous()
+                                 and obs_x.numel() == self.B * self.N * self.F)
+        self.desc.obs_x = obs_x.data_ptr() if obs_x is not None else None
         if pipelined and st.cuda_stream != 0 and h_mask is None:
             args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
                     _ptr(h_cost), _ptr(h_mask_bits), int(chunks), C.c_void_p(st.cuda_stream))
@@ -484,7 +489,7 @@ class BatchedGraphEnv:
                     _ptr(h_cost), _ptr(h_mask), _ptr(h_mask_bits), C.c_void_p(st.cuda_stream))
             fn = self.lib.ge_step_host
         check = _native.check
-        keep = (h_actions, h_reward, h_flags, h_cost, h_mask, h_mask_bits, st)
+        keep = (h_actions, h_reward, h_flags, h_cost, h_mask, h_mask_bits, st, obs_x)
 
         def call():
             check(fn(*args))

@@ -251,9 +251,15 @@ __device__ __forceinline__ float node_value(const ge_batch &d, int b, int v, int
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float *__restrict__ out, int L, float *__restrict__ out_e,
-                                                long long *__restrict__ out_i) {
-    const int b = env_lo + blockIdx.x;
+__global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, int count, float *__restrict__ out, int L, float *__restrict__ out_e,
+                                                long long *__restrict__ out_i, int warp_per_env) {
+    // One CTA per env, or -- small graphs, where a CTA per env is ~1 KB of output behind a block launch (65,536 blocks of two
+    // trips each at config 2: 138 us for 92 MB) -- one WARP per env, eight envs per CTA.  (gt, gn) = this thread's index in / the
+    // size of the group that writes one env.
+    const int gn = warp_per_env ? 32 : (int)blockDim.x, gt = warp_per_env ? ((int)threadIdx.x & 31) : (int)threadIdx.x;
+    const int slot = warp_per_env ? (int)blockIdx.x * ((int)blockDim.x >> 5) + ((int)threadIdx.x >> 5) : (int)blockIdx.x;
+    if (slot >= count) return;
+    const int b = env_lo + slot;
     const int N = d.N, M = d.M, kind = d.kind;
     int dyn;
     switch (kind) {
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     }
     const int F = dyn + 5, Fe = is_edge_kind(kind) ? 2 : 1;
     const int NF = N * F, MF = M * Fe;
-    float *o = out + (size_t)blockIdx.x * (MODE == 0 ? (size_t)L : (size_t)NF);  // the flat vector, or the node section
+    float *o = out + (size_t)slot * (MODE == 0 ? (size_t)L : (size_t)NF);  // the flat vector, or the node section
     const uint32_t *vis = d.node_bits + (size_t)b * d.NW;
     const uint32_t *aux = d.node_bits2 ? d.node_bits2 + (size_t)b * d.NW : nullptr;
     const uint32_t *tgt = d.target_bits ? d.target_bits + (size_t)b * d.NW : nullptr;
@@ -273,22 +279,22 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     const int src = seeded ? d.src[b] : 0, dest = seeded ? d.dest[b] : 0;
     const float maxd = (kind == GE_MULTICAST_ROUTING || kind == GE_PERISHABLE_DELIVERY) ? d.max_dist32[b] : 0.f;
     {   // node section: element i = (v, c) with v = i / F; the pair advances by (blockDim / F, blockDim % F) per trip
-        int v = (int)threadIdx.x / F, c = (int)threadIdx.x - v * F;
-        const int dv = (int)blockDim.x / F, dc = (int)blockDim.x - dv * F;
-        for (int i = threadIdx.x; i < NF; i += blockDim.x) {
+        int v = gt / F, c = gt - v * F;
+        const int dv = gn / F, dc = gn - dv * F;
+        for (int i = gt; i < NF; i += gn) {
             o[i] = node_value(d, b, v, c, dyn, vis, aux, tgt, src, dest, maxd);
             v += dv; c += dc;
             if (c >= F) { c -= F; ++v; }
         }
     }
     if (MODE == 2) return;
-    float *oe = MODE == 0 ? o + NF : out_e + (size_t)blockIdx.x * MF;
+    float *oe = MODE == 0 ? o + NF : out_e + (size_t)slot * MF;
     {   // edge feature section: column 0 = weight (1 for the unweighted kinds), column 1 = IS_TAKEN (Multicast) / zeros
         const bool unit = kind == GE_MAX_INDEPENDENT_SET || kind == GE_DENSEST_SUBGRAPH;
         const float *w32 = d.w32 ? d.w32 + (size_t)b * d.MP : nullptr;
         const double *w64 = d.w64 ? d.w64 + (size_t)b * d.MP : nullptr;
         const uint32_t *eb = kind == GE_MULTICAST_ROUTING ? d.edge_bits + (size_t)b * d.MW : nullptr;
-        for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        for (int e = gt; e < M; e += gn) {
             const float w = unit ? 1.f : (w32 ? w32[e] : (float)w64[e]);
             if (Fe == 1) oe[e] = w;
             else {
@@ -301,9 +307,9 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, float 
     {   // edge_links section: (source, destination) per directed edge, CSR order; one warp per row
         const int32_t *rp = d.row_ptr + (size_t)b * d.RP;
         const int32_t *col = d.col + (size_t)b * d.MP;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        const int warp = warp_per_env ? 0 : (int)threadIdx.x >> 5, lane = threadIdx.x & 31, nw = gn >> 5;
         float *ol = o + NF + MF;
-        long long *oi = out_i + (size_t)blockIdx.x * 2 * M;
+        long long *oi = out_i + (size_t)slot * 2 * M;
         for (int u = warp; u < N; u += nw) {
             const int lo = rp[u], hi = rp[u + 1];
             for (int e = lo + lane; e < hi; e += 32) {
@@ -710,12 +716,19 @@ int ge_obs_len(const ge_batch *d) {
     return d->N * (dyn + 5) + d->M * Fe + 2 * d->M;
 }
 
+// obs_kernel launch shape: elements one env's group writes (mode 2: the node section only) decide between a warp and a CTA per env
+static int obs_warp_per_env(const ge_batch *d, int mode) {
+    const int nf = ge_obs_len(d) - (is_edge_kind(d->kind) ? 4 : 3) * d->M;
+    return (mode == 2 ? nf : ge_obs_len(d)) <= 2048 ? 1 : 0;
+}
+static int obs_blocks(const ge_batch *d, int count, int mode) { return obs_warp_per_env(d, mode) ? (count + 7) / 8 : count; }
+
 int ge_obs_flat(const ge_batch *d, int env_lo, int count, float *out, void *stream) {
     GE_NVTX("ge_obs_flat");
     int rc = check_batch(d);
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
-    obs_kernel<0><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, out, ge_obs_len(d), nullptr, nullptr);
+    obs_kernel<0><<<obs_blocks(d, count, 0), 256, 0, (cudaStream_t)stream>>>(*d, env_lo, count, out, ge_obs_len(d), nullptr, nullptr, obs_warp_per_env(d, 0));
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }
@@ -726,7 +739,7 @@ int ge_obs_graph(const ge_batch *d, int env_lo, int count, float *x, float *edge
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
     if (!x || !edge_attr || !edge_index) return fail(GE_ERR_ARG, "null output buffers");
-    obs_kernel<1><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), edge_attr, (long long *)edge_index);
+    obs_kernel<1><<<obs_blocks(d, count, 1), 256, 0, (cudaStream_t)stream>>>(*d, env_lo, count, x, ge_obs_len(d), edge_attr, (long long *)edge_index, obs_warp_per_env(d, 1));
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }
@@ -737,7 +750,7 @@ int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *strea
     if (rc) return rc;
     if (env_lo < 0 || count <= 0 || env_lo + count > d->B) return fail(GE_ERR_ARG, "bad env range");
     if (!x) return fail(GE_ERR_ARG, "null output buffer");
-    obs_kernel<2><<<count, 256, 0, (cudaStream_t)stream>>>(*d, env_lo, x, ge_obs_len(d), nullptr, nullptr);
+    obs_kernel<2><<<obs_blocks(d, count, 2), 256, 0, (cudaStream_t)stream>>>(*d, env_lo, count, x, ge_obs_len(d), nullptr, nullptr, obs_warp_per_env(d, 2));
     GE_CUDA_OK(cudaGetLastError());
     return GE_OK;
 }
@@ -904,6 +917,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
     ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_cnt, 8); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
     ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);
+    ADV(obs_x, ge_obs_len(d) - (size_t)(is_edge_kind(d->kind) ? 4 : 3) * d->M);   // N * F floats per env
 #undef ADV
     return GE_OK;   // dfa is shared by the whole batch; acc keeps the parent's component stride
 }
@@ -985,12 +999,10 @@ static int pipelined_copy_in(const ge_batch *d, int lo, int n, const int32_t *h_
     GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     return GE_OK;
 }
-static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s,
-                          uint32_t *h_mask_bits = nullptr) {
+static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
     ge_batch sl;
     int rc = ge_batch_slice(d, lo, n, &sl);
     if (rc) return rc;
-    if (h_mask_bits) sl.mask_mirror = h_mask_bits + (size_t)lo * d->AW;   // direct mode: the kernel stores the packed mask on both sides
     ge_step_out so = {out->reward + lo, out->flags + lo, out->solution_cost + lo};
     return ge_step(&sl, d_actions + lo, &so, (void *)s);
 }
@@ -1004,6 +1016,10 @@ static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_
                                             h_reward + lo, h_flags + lo, h_solution_cost ? h_solution_cost + lo : nullptr,
                                             h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
     GE_CUDA_OK(cudaGetLastError());
+    if (d->obs_x) {   // node columns of the slice's observation, on the same lane (runs while the next slice steps)
+        int rc = ge_obs_nodes(d, lo, n, d->obs_x + (size_t)lo * (ge_obs_len(d) - (size_t)(is_edge_kind(d->kind) ? 4 : 3) * d->M), (void *)s);
+        if (rc) return rc;
+    }
     return GE_OK;
 }
 
@@ -1029,17 +1045,15 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
         // three-lane sequence for the following calls
         const bool zc = env_flag("GE_PIPE_ZC", &g_pipe_zc, true);
-        // direct mode (GE_PIPE_DIRECT=1, experiment): no write-back kernels -- the step kernels store reward / flags / solution_cost /
-        // packed mask straight into the pinned host arrays (coalesced 128-256 byte PCIe writes per warp)
-        static int g_pipe_direct = -1;
-        const bool direct = zc && env_flag("GE_PIPE_DIRECT", &g_pipe_direct) && ge_mask_mirror_supported(d) && h_solution_cost && h_mask_bits;
-        const ge_step_out host_out = {h_reward, h_flags, h_solution_cost};
+        // (Step kernels storing reward / flags / solution_cost / packed mask straight into the pinned host arrays -- no write-back
+        //  kernels -- measured 99-111 us per 65,536-env step against 55-59 us: 4-8 byte stores per lane reach PCIe as 32-byte
+        //  sectors, the write-back kernel's 16 bytes per lane as full lines.  profiles/r02_e2e_direct_writes.jsonl)
         const int32_t *acts = zc ? h_actions : d_actions;
         for (int i = 0; i < chunks; ++i) {
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
             if (!zc && (rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
-            if ((rc = pipelined_step(d, lo, n, acts, direct ? &host_out : out, st, direct ? h_mask_bits : nullptr))) return rc;
-            if (!direct && (rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
+            if ((rc = pipelined_step(d, lo, n, acts, out, st))) return rc;
+            if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lock(g_hsg_mu);
@@ -1069,8 +1083,7 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
                     rc2 = pipelined_copy_in(d, lo, n, h_actions, d_actions, s_in);
                     ok = ok && cudaEventRecord(g_in[i], s_in) == cudaSuccess && cudaStreamWaitEvent(st, g_in[i], 0) == cudaSuccess;
                 }
-                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, direct ? &host_out : out, st, direct ? h_mask_bits : nullptr);
-                if (direct) continue;
+                if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, out, st);
                 ok = ok && cudaEventRecord(g_stepped[i], st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_stepped[i], 0) == cudaSuccess;
                 if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s_out);
             }

@@ -180,6 +180,9 @@ typedef struct ge_batch {
     uint32_t *env_steps;          /* [B]      per-env count of accepted steps, or NULL.  ge_step increments it and the
                                               samplers add it to `t`, so a captured CUDA graph (frozen kernel
                                               arguments) draws fresh actions on every replay */
+    float *obs_x;                 /* [B, N, F] optional DEVICE buffer, or NULL: ge_step_host_pipelined rewrites the node columns of the
+                                              observation (ge_obs_nodes; utils.py:14-23 `x`) of every slice on its write-back lane, while
+                                              the next slice steps -- the dynamic part of the observation for a device-resident consumer */
 } ge_batch;
 
 /* step outputs (device pointers) */

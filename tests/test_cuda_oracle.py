@@ -268,12 +268,15 @@ def test_pipelined_host_step_equals_single_pass(cfg):
         h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
         side = torch.cuda.Stream()
         torch.cuda.synchronize()
-        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3)
+        xbuf = torch.zeros((B, N, e.F), dtype=torch.float32, device="cuda") if pipelined else None
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3, obs_x=xbuf)
         log = []
         for t in range(T):
             h_act.copy_(e.sample_actions(9, t).cpu())
             torch.cuda.synchronize()
             stepper()
+            if pipelined:   # ge_batch.obs_x: the call also rewrote the observation's node columns, slice by slice
+                assert torch.equal(xbuf, e.obs_nodes()), "obs_x must hold the node columns of the state after the step"
             assert torch.equal(h_bits, e.t["mask_bits"].cpu()), "host mask must equal the device mask after the call"
             assert torch.equal(h_rew, e.reward.cpu()) and torch.equal(h_flg, e.flags.cpu())
             log.append((h_rew.clone(), h_flg.clone(), h_cost.clone(), h_bits.clone()))
