@@ -105,7 +105,8 @@ def layout_bytes_per_step(env):
         # round 2 (csrc/ge_dc.cu): ~27 rows are expanded at N=500 E=4000 c=1, and of a weight-sorted row only the prefix that
         # can stay within the cutoff is read (~45 % of it), 4 bytes per edge (col | code)
         rows = 27 if (N == 500 and M == 8000) else max(1.0, min(N, 1 + deg + deg * deg * 0.06))
-        graph = rows * (8 + 0.45 * deg * 4) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
+        # (with ge_batch.dc_rows the rows sit at a fixed stride: no row_ptr pair per expanded row)
+        graph = rows * ((0 if env.t.get("dc_rows") is not None else 8) + 0.45 * deg * 4) + 0.5 * d.n_targets * (nw4 + 4) + 4 + 4 * nw4
     elif k == "DensestSubgraph-v0":
         graph = nw4 + 16 + 2 * nw4
     elif k == "PerishableProductDelivery-v0":

@@ -7,6 +7,7 @@ All state tensors are torch tensors on the device and are exposed as zero-copy v
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -23,7 +24,7 @@ def _ptr(t):
 
 class BatchedGraphEnv:
     def __init__(self, env_id, num_envs, n_nodes, n_edges=-1, *, device=None, byte_mask=True, auto_reset=False,
-                 structural_features=False, env_id0=0, keep_w64=True, force_warp=False, dc_transposed=False, **kwargs):
+                 structural_features=False, env_id0=0, keep_w64=True, force_warp=False, dc_transposed=False, dc_rows=True, **kwargs):
         self.lib = _native.lib()  # raises when the CUDA library is absent -- no fallback
         if not torch.cuda.is_available():
             raise _native.NativeError("graphenvs_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -36,6 +37,7 @@ class BatchedGraphEnv:
         self.M = 2 * self.E
         self.is_eval_env = bool(P.get("is_eval_env", False))
         self.structural_features = bool(structural_features)
+        self._dc_rows = bool(dc_rows) and os.environ.get("GE_DC_ROWS", "1") != "0"   # (GE_DC_ROWS=0: A/B runs)  DistributionCenter: fixed-stride copy of the weight-sorted rows (64 KB per env at N=500)
         d = _native.GeBatch()
         d.kind, d.B, d.N, d.M = self.spec.kind, self.B, self.N, self.M
         d.parenting = int(P.get("parenting", -1))
@@ -145,7 +147,7 @@ class BatchedGraphEnv:
 
     # ------------------------------------------------------------------ plumbing
     def _sync_desc(self):
-        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "dc_edges", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
+        for name in ("row_ptr", "col", "w32", "w64", "adj_bits", "rev", "esrc", "bestkey", "wsort", "wcode", "dfa", "dc_edges", "dc_rows", "wmin", "wmat", "src", "dest", "target_bits", "node_cost", "node_xy",
                      "max_dist32", "targets", "in_range", "in_range_t", "heuristic", "heuristic_alt", "features", "head", "node_bits", "node_bits2",
                      "edge_bits", "dist32", "cost", "counters", "done", "mask_bits", "mask_cnt", "mask_bytes", "mask0_bits", "acc", "traj"):
             t = self.t.get(name)
@@ -290,7 +292,7 @@ class BatchedGraphEnv:
         every edge weight of the batch is one of <= 15 distinct doubles (k/10 in the reference) and the closure of
         left-fold sums within the cutoff has < 255 values; otherwise the fp64 search stays in charge."""
         T, d, B, M = self.t, self.desc, self.B, self.M
-        for k in ("wcode", "dfa", "dc_edges"):
+        for k in ("wcode", "dfa", "dc_edges", "dc_rows"):
             T.pop(k, None)
         self._sync_desc()
         self.desc.dfa_bytes = 0
@@ -336,6 +338,8 @@ class BatchedGraphEnv:
         T["dfa"] = torch.from_numpy(np.concatenate([np.array([S, W], dtype=np.uint8), tab.ravel(), expand, cmax])).to(self.device)
         if self.N <= 1024 and self.N < 65536:
             T["dc_edges"] = torch.zeros((B, d.MP), dtype=torch.int32, device=self.device)   # weight-sorted rows for csrc/ge_dc.cu
+            if self._dc_rows:                                                                # the same rows at a fixed 128-byte stride
+                T["dc_rows"] = torch.zeros((B, self.N, 32), dtype=torch.int32, device=self.device)
         self._sync_desc()
         self.desc.dfa_bytes = int(T["dfa"].numel())
         return True

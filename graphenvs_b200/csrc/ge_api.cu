@@ -917,6 +917,7 @@ int ge_batch_slice(const ge_batch *d, int lo, int count, ge_batch *o) {
     ADV(head, 1); ADV(node_bits, d->NW); ADV(node_bits2, d->NW); ADV(edge_bits, d->MW); ADV(dist32, d->N); ADV(bestkey, d->N);
     ADV(cost, 1); ADV(counters, 4); ADV(done, 1); ADV(mask_bits, d->AW); ADV(mask_cnt, 8); ADV(mask_bytes, d->AP); ADV(mask_mirror, d->AW);
     ADV(mask0_bits, d->AW); ADV(acc, 1); ADV(traj, 1); ADV(env_steps, 1);
+    ADV(dc_rows, (size_t)d->N * 32);
     ADV(obs_x, ge_obs_len(d) - (size_t)(is_edge_kind(d->kind) ? 4 : 3) * d->M);   // N * F floats per env
 #undef ADV
     return GE_OK;   // dfa is shared by the whole batch; acc keeps the parent's component stride

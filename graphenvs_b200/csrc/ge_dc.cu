@@ -116,6 +116,76 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
     }
 }
 
+// The same search over ge_batch.dc_rows: the first DC_ROW entries of every weight-sorted row at a fixed stride (128 bytes,
+// 0xffffffff-padded, code 0xffff is beyond every prefix).  No row_ptr lookup -- the row address follows from the node id, one
+// dependent memory round less per level -- sector-aligned rows, and the row's first sector is prefetched into L2 when
+// its node is queued.  The first pass of the NEXT four rows is loaded while the current four are relaxed.  A prefix longer
+// than DC_ROW entries (a node of degree > 32 whose whole row is within the cutoff) continues in the CSR copy (rp / edges).
+#define DC_ROW 32
+__device__ __forceinline__ void dc_cutoff_search_rows(const ge_batch &d, const int32_t *__restrict__ rp, const uint32_t *__restrict__ edges,
+                                                      const uint32_t *__restrict__ rows, const uint8_t *tab, const uint8_t *expand,
+                                                      const uint8_t *cmax, int W, DcScr &s, int lane, int source) {
+    const int N = d.N, NW = d.NW;
+    {   // q[v] = 255
+        uint4 *q4 = reinterpret_cast<uint4 *>(s.q);
+        const uint4 f = make_uint4(255u, 255u, 255u, 255u);
+        for (int i = lane; i < (N + 3) >> 2; i += 32) q4[i] = f;      // the slice is padded to whole quads
+        if (lane < NW) { s.reach[lane] = 0; s.queued[lane] = 0; }
+    }
+    __syncwarp();
+    if (lane == 0) { s.q[source] = 0u; s.reach[source >> 5] = 1u << (source & 31); s.cur[0] = (uint16_t)source; *s.cnt = 0; }
+    __syncwarp();
+    int ncur = expand[0] ? 1 : 0;
+    const int grp = lane >> 3, gl = lane & 7;
+    uint16_t *cur = s.cur, *nxt = s.nxt;
+    while (ncur > 0) {
+        int u = grp < ncur ? (int)cur[grp] : -1;
+        uint32_t pk = u >= 0 ? rows[(size_t)u * DC_ROW + gl] : 0xffffffffu;      // first pass of the first four rows
+        for (int i0 = 0; i0 < ncur; i0 += 4) {
+            const int u_n = i0 + 4 + grp < ncur ? (int)cur[i0 + 4 + grp] : -1;   // next four rows: first pass in flight now
+            const uint32_t pk_n = u_n >= 0 ? rows[(size_t)u_n * DC_ROW + gl] : 0xffffffffu;
+            const int du = u >= 0 ? (int)s.q[u] : 0;
+            const uint8_t *trow = tab + du * W;
+            const uint32_t cm = u >= 0 ? (uint32_t)cmax[du] : 255u;             // 255 = nothing within the cutoff
+            for (int k = gl;; k += 8) {
+                const uint32_t code = pk >> 16;
+                const bool act = cm != 255u && code <= cm;                       // padding has code 0xffff
+                if (act) {
+                    const int v = (int)(pk & 0xffffu);
+                    const uint32_t nid = trow[code];                             // state of fl(dist + w); inside the prefix => never 255
+                    if (nid < s.q[v]) {
+                        const uint32_t old = atomicMin(&s.q[v], nid);
+                        if (nid < old) {
+                            const uint32_t bit = 1u << (v & 31);
+                            if (old == 255u) atomicOr(&s.reach[v >> 5], bit);
+                            if (expand[nid] && !(atomicOr(&s.queued[v >> 5], bit) & bit)) {
+                                nxt[atomicAdd(s.cnt, 1)] = (uint16_t)v;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + (size_t)v * DC_ROW));   // next round's row
+                            }
+                        }
+                    }
+                }
+                const unsigned cont = __ballot_sync(GE_FULL, act && gl == 7);    // bit 8g + 7: row g filled its whole pass => it continues
+                if (!cont) break;                                                // every prefix is exhausted
+                const int kn = k + 8;
+                pk = 0xffffffffu;
+                if ((cont >> ((lane & ~7) | 7)) & 1u) {
+                    if (kn < DC_ROW) pk = rows[(size_t)u * DC_ROW + kn];
+                    else { const int e = rp[u] + kn; if (e < rp[u + 1]) pk = edges[e]; }
+                }
+            }
+            u = u_n; pk = pk_n;
+        }
+        __syncwarp();
+        ncur = *s.cnt;
+        __syncwarp();
+        if (lane == 0) *s.cnt = 0;
+        if (lane < NW) s.queued[lane] = 0;
+        uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+        __syncwarp();
+    }
+}
+
 // OR of the in-range rows of the targets that are not covered yet (distribution_center.py:129-141, parenting 2).
 // covw = the lane's word of the covered set.  Returns the lane's word of the union (lanes >= NW: 0).
 __device__ __forceinline__ uint32_t dc_union_in_range(const ge_batch &d, int b, int lane, uint32_t covw, uint16_t *live /* >= n_targets */) {
@@ -280,7 +350,8 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
         cost = (double)__fadd_rn((float)cost, w);
         float rew = -w;
         if (lane == (a >> 5)) takenw |= 1u << (a & 31);
-        dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, tab, expand, cmax, W, s, lane, a);
+        if (d.dc_rows) dc_cutoff_search_rows(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, d.dc_rows + (size_t)b * N * DC_ROW, tab, expand, cmax, W, s, lane, a);
+        else dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, tab, expand, cmax, W, s, lane, a);
         const uint32_t reachw = WL ? s.reach[lane] : 0u;                          // find_nodes_in_range (:25-26,155)
         const int gained = __reduce_add_sync(GE_FULL, __popc(reachw & ~covw & tgtw));
         covw |= reachw;
@@ -370,6 +441,10 @@ __global__ void __launch_bounds__(256) dc_edges_kernel(ge_batch d) {
     for (int c = 0; c < 16 && pos < hi; ++c)                       // at most 15 distinct weights (batch.py:_build_distance_automaton)
         for (int e = lo; e < hi; ++e)
             if (wc[e] == c) out[pos++] = (uint32_t)col[e] | ((uint32_t)c << 16);
+    if (d.dc_rows) {                                               // the same row at a fixed stride, padded
+        uint32_t *row = d.dc_rows + ((size_t)b * d.N + u) * 32;
+        for (int k = 0; k < 32; ++k) row[k] = (lo + k < hi) ? out[lo + k] : 0xffffffffu;
+    }
 }
 
 // in_range_t[v] bit t = in_range[t] bit v (128 targets per node).  One warp per env.

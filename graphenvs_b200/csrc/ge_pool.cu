@@ -103,7 +103,7 @@ extern "C" int ge_pool_refill(const ge_batch *live, const ge_batch *banks, int n
 #define POOL_ADD(field, bytes) if (rc == GE_OK) rc = add(d.field, offsetof(ge_batch, field), (size_t)(bytes), false)
     POOL_ADD(row_ptr, d.RP * 4); POOL_ADD(col, d.MP * 4); POOL_ADD(w32, d.MP * 4); POOL_ADD(w64, d.MP * 8);
     if (rc == GE_OK) rc = add(d.adj_bits, offsetof(ge_batch, adj_bits), adj_tiled(d) ? 4 : (size_t)d.ADJS * 4, adj_tiled(d));
-    POOL_ADD(rev, d.MP * 4); POOL_ADD(esrc, d.MP * 4); POOL_ADD(wsort, d.MP * 8); POOL_ADD(wcode, d.MP); POOL_ADD(dc_edges, d.MP * 4); POOL_ADD(wmin, 8);
+    POOL_ADD(rev, d.MP * 4); POOL_ADD(esrc, d.MP * 4); POOL_ADD(wsort, d.MP * 8); POOL_ADD(wcode, d.MP); POOL_ADD(dc_edges, d.MP * 4); POOL_ADD(dc_rows, (size_t)d.N * 128); POOL_ADD(wmin, 8);
     POOL_ADD(wmat, (size_t)d.N * d.N * 8); POOL_ADD(src, 4); POOL_ADD(dest, 4); POOL_ADD(target_bits, d.NW * 4);
     POOL_ADD(node_cost, d.N * 4); POOL_ADD(node_xy, d.N * 8); POOL_ADD(max_dist32, 4); POOL_ADD(targets, d.n_targets * 4);
     POOL_ADD(in_range, (size_t)d.n_targets * d.NW * 4); POOL_ADD(in_range_t, (size_t)d.N * 16); POOL_ADD(heuristic, 8); POOL_ADD(heuristic_alt, 8);

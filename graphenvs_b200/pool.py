@@ -27,7 +27,8 @@ class InstancePool:
         for k in range(self.G):
             b = BatchedGraphEnv(env.env_id, env.B, n_nodes, n_edges, device=env.device, byte_mask=False, auto_reset="mask0_bits" in env.t,
                                 structural_features=env.structural_features, env_id0=env.desc.env_id0,
-                                force_warp=bool(env.desc.flags & 8), **P)
+                                force_warp=bool(env.desc.flags & 8), dc_rows="dc_rows" in env.t,
+                                dc_transposed="in_range_t" in env.t, **P)
             b.generate(seed=self._next_seed(), check=False)
             if "mask0_bits" in b.t:
                 b.reset()                       # fills mask0_bits (the first mask depends only on the instance)

@@ -183,6 +183,11 @@ typedef struct ge_batch {
     float *obs_x;                 /* [B, N, F] optional DEVICE buffer, or NULL: ge_step_host_pipelined rewrites the node columns of the
                                               observation (ge_obs_nodes; utils.py:14-23 `x`) of every slice on its write-back lane, while
                                               the next slice steps -- the dynamic part of the observation for a device-resident consumer */
+    uint32_t *dc_rows;            /* [B, N, 32] DistributionCenter with an automaton, optional (derived by ge_prepare bit 4 next to dc_edges):
+                                              the first 32 entries of every weight-sorted row at a FIXED stride of 128 bytes, padded with
+                                              0xffffffff.  The cutoff search then needs no row_ptr lookup (one dependent memory round
+                                              less per search level), reads sector-aligned rows, and prefetches a row when its node is
+                                              queued; a prefix longer than 32 entries continues in dc_edges */
 } ge_batch;
 
 /* step outputs (device pointers) */

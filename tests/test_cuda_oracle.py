@@ -59,6 +59,7 @@ CONFIGS = [
     ("MulticastRouting-v0", 40, 120, {"parenting": 1, "n_dests": 3}, 20),
     ("DistributionCenter-v0", 120, 500, {"parenting": 2}, 40),
     ("DistributionCenter-v0", 90, 300, {"parenting": 1, "max_distance": 1.2}, 40),
+    ("DistributionCenter-v0", 80, 1500, {"parenting": 2, "target_count": 20}, 30),   # degree ~37 > 32: prefixes continue past the fixed-stride rows (dc_rows)
     ("PerishableProductDelivery-v0", 40, 100, {"n_products": 3, "parenting": 1}, 400),
     ("PerishableProductDelivery-v0", 300, 900, {"n_products": 5, "parenting": 1}, 300),
     ("PerishableProductDelivery-v0", 12, 20, {"n_products": 5, "parenting": 1, "weighted": False}, 3200),   # runs into max_steps = N * P * 50
@@ -327,6 +328,30 @@ def test_obs_nodes_is_the_x_tensor_of_obs_graph():
         assert torch.equal(env.obs_nodes(7, 11), x[7:18])
         name = env.step_kernel_name(sampled=True)
         assert name.endswith(">") and "step_kernel<" in name
+
+
+@pytest.mark.parametrize("shape", [(120, 500), (80, 1500), (500, 4000)], ids=["sparse", "degree>32", "cfg5"])
+def test_distribution_center_fixed_stride_rows_equal_csr_rows(shape):
+    """ge_batch.dc_rows (weight-sorted rows at a fixed 128-byte stride, no row_ptr lookups) is a layout choice: same
+    trajectories, masks and covered sets as the search over the CSR copy (dc_edges)."""
+    N, E = shape
+    B, T = 256, 40
+    envs = []
+    for rows in (False, True):
+        e = BatchedGraphEnv("DistributionCenter-v0", B, N, E, parenting=2, target_count=min(100, N // 4), max_distance=1, auto_reset=True, dc_rows=rows)
+        e.generate(seed=21)
+        e.reset()
+        assert ("dc_rows" in e.t) == rows and e.step_kernel_name() .startswith("dc_step_kernel")
+        for t in range(T):
+            e.step_sampled(4, t)
+        torch.cuda.synchronize()
+        envs.append(e)
+    a, b = envs
+    if N == 80:
+        deg = (a.t["row_ptr"][:, 1:N + 1] - a.t["row_ptr"][:, :N]).max().item()
+        assert deg > 32, "this shape is meant to overflow the 32-entry rows"
+    for k in ("traj", "mask_bits", "node_bits", "node_bits2", "cost", "acc", "done"):
+        assert torch.equal(a.t[k], b.t[k]), k
 
 
 def test_distribution_center_transposed_mask_equals_row_union():
