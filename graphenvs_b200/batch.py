@@ -104,7 +104,7 @@ class BatchedGraphEnv:
         if env_id == "DistributionCenter-v0":
             T["targets"] = z((B, max(d.n_targets, 1)), torch.int32)
             T["in_range"] = z((B, max(d.n_targets, 1), d.NW), torch.int32)
-            if dc_transposed and 0 < d.n_targets <= 128 and N <= 1024 and not force_warp and int(P.get("parenting", 2)) == 2:
+            if (dc_transposed or os.environ.get("GE_DC_TRANSPOSED") == "1") and 0 < d.n_targets <= 128 and N <= 1024 and not force_warp and int(P.get("parenting", 2)) == 2:
                 # transposed table (per node the targets that have it in range): an alternative mask build measured
                 # equal in time with 16 % more HBM traffic at config 5, hence off by default
                 T["in_range_t"] = z((B, N, 4), torch.int32)

@@ -122,7 +122,7 @@ __device__ __forceinline__ void dc_cutoff_search(const ge_batch &d, const int32_
 // its node is queued.  The first pass of the NEXT four rows is loaded while the current four are relaxed.  A prefix longer
 // than DC_ROW entries (a node of degree > 32 whose whole row is within the cutoff) continues in the CSR copy (rp / edges).
 #define DC_ROW 32
-__device__ __forceinline__ void dc_cutoff_search_rows(const ge_batch &d, const int32_t *__restrict__ rp, const uint32_t *__restrict__ edges,
+__device__ __forceinline__ uint32_t dc_cutoff_search_rows(const ge_batch &d, const int32_t *__restrict__ rp, const uint32_t *__restrict__ edges,
                                                       const uint32_t *__restrict__ rows, const uint8_t *tab, const uint8_t *expand,
                                                       const uint8_t *cmax, int W, DcScr &s, int lane, int source) {
     const int N = d.N, NW = d.NW;
@@ -138,6 +138,26 @@ __device__ __forceinline__ void dc_cutoff_search_rows(const ge_batch &d, const i
     int ncur = expand[0] ? 1 : 0;
     const int grp = lane >> 3, gl = lane & 7;
     uint16_t *cur = s.cur, *nxt = s.nxt;
+    // one edge entry against the automaton: returns whether it was inside the prefix of its row
+    auto relax = [&](uint32_t pk, uint32_t cm, const uint8_t *trow) -> bool {
+        const uint32_t code = pk >> 16;
+        const bool act = code <= cm;                                             // padding has code 0xffff; cm = 0xfffe0000 >> 16 never
+        if (act) {
+            const int v = (int)(pk & 0xffffu);
+            const uint32_t nid = trow[code];                                     // state of fl(dist + w); inside the prefix => never 255
+            if (nid < s.q[v]) {
+                const uint32_t old = atomicMin(&s.q[v], nid);
+                if (nid < old) {
+                    const uint32_t bit = 1u << (v & 31);
+                    if (expand[nid] && !(atomicOr(&s.queued[v >> 5], bit) & bit)) {
+                        nxt[atomicAdd(s.cnt, 1)] = (uint16_t)v;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + (size_t)v * DC_ROW));   // next round's row
+                    }
+                }
+            }
+        }
+        return act;
+    };
     while (ncur > 0) {
         int u = grp < ncur ? (int)cur[grp] : -1;
         uint32_t pk = u >= 0 ? rows[(size_t)u * DC_ROW + gl] : 0xffffffffu;      // first pass of the first four rows
@@ -146,32 +166,25 @@ __device__ __forceinline__ void dc_cutoff_search_rows(const ge_batch &d, const i
             const uint32_t pk_n = u_n >= 0 ? rows[(size_t)u_n * DC_ROW + gl] : 0xffffffffu;
             const int du = u >= 0 ? (int)s.q[u] : 0;
             const uint8_t *trow = tab + du * W;
-            const uint32_t cm = u >= 0 ? (uint32_t)cmax[du] : 255u;             // 255 = nothing within the cutoff
-            for (int k = gl;; k += 8) {
-                const uint32_t code = pk >> 16;
-                const bool act = cm != 255u && code <= cm;                       // padding has code 0xffff
-                if (act) {
-                    const int v = (int)(pk & 0xffffu);
-                    const uint32_t nid = trow[code];                             // state of fl(dist + w); inside the prefix => never 255
-                    if (nid < s.q[v]) {
-                        const uint32_t old = atomicMin(&s.q[v], nid);
-                        if (nid < old) {
-                            const uint32_t bit = 1u << (v & 31);
-                            if (old == 255u) atomicOr(&s.reach[v >> 5], bit);
-                            if (expand[nid] && !(atomicOr(&s.queued[v >> 5], bit) & bit)) {
-                                nxt[atomicAdd(s.cnt, 1)] = (uint16_t)v;
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + (size_t)v * DC_ROW));   // next round's row
-                            }
-                        }
-                    }
-                }
-                const unsigned cont = __ballot_sync(GE_FULL, act && gl == 7);    // bit 8g + 7: row g filled its whole pass => it continues
+            uint32_t cm = u >= 0 ? (uint32_t)cmax[du] : 255u;
+            if (cm == 255u) { cm = 0u; pk = 0xffffffffu; }                       // 255 = nothing within the cutoff: an all-padding row
+            const uint32_t *row = rows + (size_t)(u >= 0 ? u : 0) * DC_ROW + gl;
+            unsigned cont = 0;
+#pragma unroll
+            for (int pass = 0; pass < DC_ROW / 8; ++pass) {
+                const bool act = relax(pk, cm, trow);
+                cont = __ballot_sync(GE_FULL, act && gl == 7);                   // bit 8g + 7: row g filled its whole pass => it continues
                 if (!cont) break;                                                // every prefix is exhausted
-                const int kn = k + 8;
                 pk = 0xffffffffu;
-                if ((cont >> ((lane & ~7) | 7)) & 1u) {
-                    if (kn < DC_ROW) pk = rows[(size_t)u * DC_ROW + kn];
-                    else { const int e = rp[u] + kn; if (e < rp[u + 1]) pk = edges[e]; }
+                if (pass + 1 < DC_ROW / 8 && ((cont >> ((lane & ~7) | 7)) & 1u)) pk = row[8 * (pass + 1)];
+            }
+            if (cont) {   // rare: a prefix longer than DC_ROW entries continues in the CSR copy
+                for (int k = DC_ROW + gl;; k += 8) {
+                    pk = 0xffffffffu;
+                    if ((cont >> ((lane & ~7) | 7)) & 1u) { const int e = rp[u] + k; if (e < rp[u + 1]) pk = edges[e]; }
+                    const bool act = relax(pk, cm, trow);
+                    cont = __ballot_sync(GE_FULL, act && gl == 7);
+                    if (!cont) break;
                 }
             }
             u = u_n; pk = pk_n;
@@ -184,6 +197,15 @@ __device__ __forceinline__ void dc_cutoff_search_rows(const ge_batch &d, const i
         uint16_t *tmp = cur; cur = nxt; nxt = tmp;
         __syncwarp();
     }
+    // reached = every node that got a state (q != 255): one ballot per word instead of
+    // an atomic per first visit.  Returned in registers, lane w = word w.
+    uint32_t mine = 0;
+    for (int w = 0; w < NW; ++w) {
+        const int v = (w << 5) + lane;
+        const unsigned bits = __ballot_sync(GE_FULL, v < N && s.q[v] != 255u);
+        if (lane == w) mine = bits;
+    }
+    return mine;
 }
 
 // OR of the in-range rows of the targets that are not covered yet (distribution_center.py:129-141, parenting 2).
@@ -350,9 +372,9 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
         cost = (double)__fadd_rn((float)cost, w);
         float rew = -w;
         if (lane == (a >> 5)) takenw |= 1u << (a & 31);
-        if (d.dc_rows) dc_cutoff_search_rows(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, d.dc_rows + (size_t)b * N * DC_ROW, tab, expand, cmax, W, s, lane, a);
-        else dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, tab, expand, cmax, W, s, lane, a);
-        const uint32_t reachw = WL ? s.reach[lane] : 0u;                          // find_nodes_in_range (:25-26,155)
+        uint32_t reachw;                                                          // find_nodes_in_range (:25-26,155)
+        if (d.dc_rows) reachw = dc_cutoff_search_rows(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, d.dc_rows + (size_t)b * N * DC_ROW, tab, expand, cmax, W, s, lane, a);
+        else { dc_cutoff_search(d, d.row_ptr + (size_t)b * d.RP, d.dc_edges + (size_t)b * d.MP, tab, expand, cmax, W, s, lane, a); reachw = WL ? s.reach[lane] : 0u; }
         const int gained = __reduce_add_sync(GE_FULL, __popc(reachw & ~covw & tgtw));
         covw |= reachw;
         rew += (float)gained;
