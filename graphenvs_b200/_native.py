@@ -144,7 +144,7 @@ def lib():
     L.ge_mask_mirror_supported.argtypes = [BP]
     L.ge_mask_bytes_current.argtypes = [BP]
     L.ge_mask_bytes.argtypes = [BP, C.c_int, C.c_int, _P]
-    if L.ge_abi_version() != 2:
+    if L.ge_abi_version() != 3:
         raise NativeError("ABI version mismatch")
     _lib = L
     return L

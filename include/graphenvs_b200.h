@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GE_ABI_VERSION 2
+#define GE_ABI_VERSION 3
 
 typedef enum {
     GE_SHORTEST_PATH = 0,      /* ShortestPath-v0        shortest_path.py        node actions */

@@ -19,18 +19,27 @@ scal = [p for p in ("r02_scaling_1gpu.json", "r02_scaling_2gpu.json", "r02_scali
 tab = subprocess.check_output([sys.executable, os.path.join(HERE, "make_table.py"), os.path.join(HERE, "r02_bench_default.json")] +
                               [os.path.join(HERE, p) for p in scal]).decode()
 e = d["e2e"]
-print("""Device numbers: everything resident, one launch per batch step (`ge_step_sampled`: uniform valid action drawn in-kernel + step +
-new mask + auto-reset), CUDA-graph replay, L2 flushed between steps, CUDA events around every step.  `e2e`: the same step through
-`ge_step_host_pipelined` with pinned host buffers (actions in; reward / flags / solution_cost / packed mask out; two slices, the
-write-back of one overlapping the kernel of the next).  CPU port: `oracle/graphenvs_oracle.c` with OpenMP over envs on the GPU box's host
-threads.  Python reference: the unmodified `graph_envs` loop as recorded on the build container (`profiles/r02_python_reference_cpu.json`).
+st = d.get("streaming") or {}
+print("""Device numbers: everything resident, the uniform valid action is drawn in the step kernel (`ge_step_sampled`: sampler + step + new
+mask + auto-reset).  **Streaming protocol** (the `value`): EXACTLY K steps in ONE timed region (one CUDA event pair, barrier + synchronize on
+both sides), no flush inside; the steps rotate over R independent resident batches of B envs, R chosen so that one rotation touches more than
+3 x L2 (every step finds its batch cold); one step of a batch = C sub-batch launches on C free-running stream chains, launched with
+programmatic dependent launch.  **Isolated protocol** (round 1's, kept beside it): a 256 MiB write + read flushes L2 before every step, each
+step between its own event pair (~6 µs of launch + event overhead inside every pair).  Workloads whose R batches do not fit in HBM (config 4) report
+the isolated protocol only.  `e2e`: the step through `ge_step_host_pipelined` with pinned host buffers (actions in; reward / flags /
+solution_cost / packed mask out; two slices, the write-back of one overlapping the kernel of the next); `e2e + obs`: the same call also rewrites
+the observation's node columns `x[B, N, F]` on the device (`ge_batch.obs_x`).  CPU port: `oracle/graphenvs_oracle.c` with OpenMP over envs on
+the GPU box's host threads.  Python reference: the unmodified `graph_envs` loop as recorded on the build container
+(`profiles/r02_python_reference_cpu.json`).
 """)
 print("**Headline** (BASELINE config 2, LongestPath N=50 E=200 p=2, 65,536 envs, 1 B200): **%.3g env-steps/s** on the device (%.1f µs per batch "
-      "step, %.2f of the measured %.0f GB/s on the %.0f bytes per env-step this layout must move; %.0f measured by ncu), **%.3g env-steps/s end to end** "
+      "step, streaming over %d batches x %d chains; %.2f of the measured %.0f GB/s on the %.0f bytes per env-step this layout must move, %.0f measured by "
+      "ncu; isolated: %.1f µs, %.2f), **%.3g env-steps/s end to end** "
       "through the C ABI with host buffers (%.3g with the device sampler choosing the actions between calls), %.3g with the observation's node "
       "columns rewritten every step; reference arm (CPU port, %d threads): %.3g env-steps/s.\n" % (
-          d["value"], 1e3 * d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["peak"], d["roofline"]["bytes_per_env_step"],
-          (d["roofline"]["traffic"] or 0) / d["config"]["envs_per_gpu"], e["value"], e.get("value_with_device_policy_between_calls") or float("nan"),
+          d["value"], 1e3 * d["ms_per_step"], st.get("replicas", 1), st.get("chunks", 1), d["roofline"]["frac"], d["roofline"]["peak"],
+          d["roofline"]["bytes_per_env_step"], (d["roofline"]["traffic"] or 0) / d["config"]["envs_per_gpu"],
+          1e3 * d["isolated"]["ms_per_step"], d["roofline"]["frac_isolated"], e["value"], e.get("value_with_device_policy_between_calls") or float("nan"),
           d["e2e_obs"]["value"], ref["cpu_baseline"]["cores"], ref["value"]))
 print(tab)
 f = d["feature_extraction_us_per_env"]

@@ -16,9 +16,9 @@ def load(path):
 
 
 d = load(sys.argv[1])
-print("| workload | envs/GPU | env-steps/s (device) | µs / batch step | B / env-step (this layout) | measured DRAM B / env-step (ncu) | frac of %.0f GB/s | e2e env-steps/s (host buffers) | CPU port env-steps/s (cores) | Python reference, 1 core / all cores | e2e ÷ CPU port |"
+print("| workload | envs/GPU | env-steps/s (device) | µs / batch step | protocol (R batches x C chains) | µs isolated (flush + event pair per step) | B / env-step (this layout) | measured DRAM B / env-step (ncu) | frac of %.0f GB/s (isolated) | e2e env-steps/s (host buffers) | e2e + obs node columns | CPU port env-steps/s (cores) | Python reference, 1 core / all cores | e2e ÷ CPU port |"
       % d["roofline"]["peak"])
-print("|---|---|---|---|---|---|---|---|---|---|---|")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for w in d["workloads"]:
     r, c, py = w["roofline"], w.get("cpu_baseline") or {}, w.get("cpu_reference_python") or {}
     tr = r.get("traffic")
@@ -26,9 +26,15 @@ for w in d["workloads"]:
     if py:
         a, b = py.get("one_core_step_only_steps_per_s"), py.get("all_cores_steps_per_s")
         pyref = "%s / %s (%s)" % ("%.3g" % a if a else "n/a", "%.3g" % b if b else "n/a", py.get("cores"))
-    print("| %s | %d | %.3g | %.1f | %.0f | %s | %.3f | %.3g | %s | %s | %s |" % (
-        w["name"], w["envs_per_gpu"], w["value"], 1e3 * w["ms_per_step"], r["bytes_per_env_step"],
-        ("%.0f" % (tr / w["envs_per_gpu"])) if tr else "-", r["frac"], w["e2e"]["value"],
+    st = w.get("streaming")
+    proto = ("streaming %d x %d" % (st["replicas"], st["chunks"])) if st else "isolated"
+    iso = w.get("isolated") or {}
+    eo = w.get("e2e_obs") or {}
+    print("| %s | %d | %.3g | %.1f | %s | %s | %.0f | %s | %.3f (%s) | %.3g | %s | %s | %s | %s |" % (
+        w["name"], w["envs_per_gpu"], w["value"], 1e3 * w["ms_per_step"], proto, ("%.1f" % (1e3 * iso["ms_per_step"])) if iso else "-",
+        r["bytes_per_env_step"], ("%.0f" % (tr / w["envs_per_gpu"])) if tr else "-", r["frac"],
+        ("%.3f" % r["frac_isolated"]) if r.get("frac_isolated") is not None else "-", w["e2e"]["value"],
+        ("%.3g" % eo["value"]) if eo else "-",
         ("%.3g (%s)" % (c["value"], c["cores"])) if c else "-", pyref, ("%.0fx" % (w["e2e"]["value"] / c["value"])) if c else "-"))
 if len(sys.argv) > 2:
     print()

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_native.EXPORTS) == syms
     lib.ge_abi_version.restype = C.c_int
-    assert lib.ge_abi_version() == 2
+    assert lib.ge_abi_version() == 3
 
 
 def test_ctypes_struct_matches_c_layout():
