@@ -521,51 +521,53 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         except Exception:
             floor_ms = None
 
-    # ---- end to end through the C ABI with host buffers (ge_step_host); the policy between calls is untimed
+    # ---- end to end through the C ABI with host buffers; the policy between calls is untimed.  Result format: compact
+    #      (ge_step_host_compact: reward f32, ONE flag byte, solution_cost f32, packed mask) or full (ge_step_host_pipelined /
+    #      ge_step_host: 4 flag bytes, solution_cost f64)
     d = env.desc
-    h_blk, h_rew, h_flg, h_cost, h_bits = env.host_io()
+    compact = args.e2e_format == "compact" and args.e2e == "pipelined"
     h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
     rng = np.random.default_rng(SEED + rank)
-    h_bits.copy_(env.t["mask_bits"])
-    torch.cuda.synchronize()
     Ke = max(3, min(K, args.e2e_steps))
-    side = torch.cuda.Stream(device=dev)       # a real stream: ge_step_host replays its copy/step/copy sequence as a graph
-    stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"), chunks=args.e2e_chunks)
-    e2e_s = 0.0
-    D.barrier()
-    for k in range(3 + Ke):
-        if host_side_policy:               # README loop on the host: uniform valid action from the mask that came back
-            mask = np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
-            h_act.numpy()[:] = host_policy(rng, mask)
-        else:                              # large action spaces (up to 8000 edges x 131072 envs): the same draw on the device, copied out
-            env.sample_actions(SEED, 7)
-            h_act.copy_(env.actions_dev)
-        flush()
+    side = torch.cuda.Stream(device=dev)       # a real stream: the host step replays its copy/step/copy sequence as a graph
+
+    def e2e_loop(use_compact, host_policy_on):
+        if use_compact:
+            h_rew, h_flg, h_cost, h_bits = env.host_io_compact()
+        else:
+            _blk, h_rew, h_flg, h_cost, h_bits = env.host_io()
+        h_bits.copy_(env.t["mask_bits"])
         torch.cuda.synchronize()
-        c0 = time.perf_counter()
-        stepper()
-        c1 = time.perf_counter()
-        if k >= 3:
-            e2e_s += c1 - c0
-        assert int(h_flg.numpy()[:, 2].max()) == 0, "policy produced an invalid action"
-    e2e_s_max = D.reduce([e2e_s], "max")[0]
-    e2e_val = envs_all * Ke / e2e_s_max
-    e2e_dev_val = None
-    if host_side_policy:       # the same call with the actions drawn by the device sampler between calls (untimed): the GPU
-        t_dev = 0.0            # does not idle for the milliseconds the numpy policy takes, which by itself costs ~10 us per call
+        stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"),
+                                   chunks=args.e2e_chunks, compact=use_compact)
+        tot = 0.0
+        D.barrier()
         for k in range(3 + Ke):
-            env.sample_actions(SEED, 7)
-            h_act.copy_(env.actions_dev)
+            if host_policy_on:                 # README loop on the host: uniform valid action from the mask that came back
+                mask = np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")[:, :d.A].astype(bool)
+                h_act.numpy()[:] = host_policy(rng, mask)
+            else:                              # large action spaces (up to 8000 edges x 131072 envs): the same draw on the device, copied out
+                env.sample_actions(SEED, 7)
+                h_act.copy_(env.actions_dev)
             flush()
             torch.cuda.synchronize()
             c0 = time.perf_counter()
             stepper()
             c1 = time.perf_counter()
             if k >= 3:
-                t_dev += c1 - c0
-        e2e_dev_val = envs_all * Ke / D.reduce([t_dev], "max")[0]
+                tot += c1 - c0
+            status = ((h_flg.numpy() >> 3) & 3) if use_compact else h_flg.numpy()[:, 2]
+            assert int(status.max()) == 0, "policy produced an invalid action"
+        return envs_all * Ke / D.reduce([tot], "max")[0], stepper, (h_rew, h_flg, h_cost, h_bits)
+
+    e2e_val, stepper, (h_rew, h_flg, h_cost, h_bits) = e2e_loop(compact, host_side_policy)
+    e2e_dev_val = e2e_full_val = None
+    if host_side_policy:       # the same call with the actions drawn by the device sampler between calls (untimed): the GPU
+        e2e_dev_val = e2e_loop(compact, False)[0]   # does not idle for the milliseconds the numpy policy takes (~10 us per call by itself)
+        if compact:            # and in the full result format (16 instead of 9 bytes per env next to the mask)
+            e2e_full_val = e2e_loop(False, True)[0]
     h2d = B * 4
-    d2h = B * 16 + B * d.AW * 4
+    d2h = B * (9 if compact else 16) + B * d.AW * 4
 
     # ---- end to end INCLUDING the observation update for a device-resident consumer: the same host step followed by
     #      ge_obs_graph of the whole batch's node columns (utils.py:14-23: x [B, N, F]); edge tensors are static / reset-time.
@@ -574,7 +576,8 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         xbuf = torch.empty((B, N, env.F), dtype=torch.float32, device=dev)
         fused_obs = args.e2e == "pipelined"
         if fused_obs:     # ge_batch.obs_x: every slice's node columns are rewritten on the write-back lane of the SAME call
-            stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True, chunks=args.e2e_chunks, obs_x=xbuf)
+            stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True, chunks=args.e2e_chunks, obs_x=xbuf,
+                                       compact=compact)
         t_obs = 0.0
         Ko = max(3, min(Ke, 20))
         for k in range(2 + Ko):
@@ -625,8 +628,11 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
                 "value_with_device_policy_between_calls": e2e_dev_val,
+                "value_full_result_format": e2e_full_val,
+                "result_format": ("compact (ge_step_host_compact): reward f32 + 1 flag byte + solution_cost f32 + packed mask" if compact
+                                  else "full: reward f32 + 4 flag bytes + solution_cost f64 + packed mask"),
                 "timed": ("sum of the host-step calls on pinned host buffers, " + (
-                    "ge_step_host_pipelined: %d slices on one CUDA graph; the step kernels read the int32 actions straight from the pinned "
+                    "ge_step_host_compact / ge_step_host_pipelined: %d slices on one CUDA graph; the step kernels read the int32 actions straight from the pinned "
                     "host buffer over PCIe (no staging copy), a write-back kernel streams each slice's reward / flags / solution_cost / packed "
                     "mask into the pinned host arrays while the next slice steps; completion polled" % args.e2e_chunks
                     if args.e2e == "pipelined" else
@@ -866,6 +872,8 @@ def main():
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"])
     ap.add_argument("--e2e", default="pipelined", choices=["pipelined", "single"],
                     help="pipelined: ge_step_host in chunks on two streams (copies overlap kernels); single: one copy-in / kernel / copy-out")
+    ap.add_argument("--e2e-format", default="compact", choices=["compact", "full"],
+                    help="host result format of the end-to-end step: compact = 1 flag byte + float32 solution_cost per env (ge_step_host_compact)")
     ap.add_argument("--e2e-device-policy", action="store_true",
                     help="headline e2e: draw the actions with the device sampler between calls (untimed) instead of the host numpy policy")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the pipelined end-to-end step")

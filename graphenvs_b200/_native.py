@@ -96,7 +96,7 @@ class StepOut(C.Structure):
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
            "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_pool_refill", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
-           "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined",
+           "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined", "ge_step_host_compact",
            "ge_step_host_release", "ge_mask_mirror_supported", "ge_mask_bytes_current", "ge_mask_bytes", "ge_stats"]
 
 _lib = None
@@ -135,6 +135,7 @@ def lib():
     L.ge_obs_graph.argtypes = [BP, C.c_int, C.c_int, _P, _P, _P, _P]
     L.ge_step_host.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, _P, _P]
     L.ge_step_host_pipelined.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, C.c_int, _P]
+    L.ge_step_host_compact.argtypes = [BP, _P, _P, C.POINTER(StepOut), _P, _P, _P, _P, C.c_int, _P]
     L.ge_step_host_release.argtypes = [BP]
     L.ge_obs_nodes.argtypes = [BP, C.c_int, C.c_int, _P, _P]
     L.ge_step_kernel_name.argtypes = [BP, C.c_int]

@@ -124,7 +124,7 @@ class BatchedGraphEnv:
         T["counters"] = z((B, 4), torch.int32)
         T["done"] = z((B,), torch.uint8)
         # step outputs + packed mask live back to back in one block => one D2H copy in ge_step_host
-        Bp = (B + 1) & ~1
+        Bp = (B + 3) & ~3                                     # every section of the block starts 16-byte aligned (128-bit copies)
         self._io = z((16 * Bp + 4 * B * d.AW,), torch.uint8)
         self._io_layout = (Bp, 16 * Bp + 4 * B * d.AW)
         T["mask_bits"] = self._io[16 * Bp:].view(torch.int32).view(B, d.AW)
@@ -472,8 +472,21 @@ class BatchedGraphEnv:
         _native.check(self.lib.ge_step_host(C.byref(self.desc), _ptr(h_actions), None, C.byref(self._out), _ptr(h_reward),
                                             _ptr(h_flags), _ptr(h_cost), None, _ptr(h_mask_bits), self._stream()))
 
+    def host_io_compact(self):
+        """Pinned host buffers of the COMPACT result format (ge_step_host_compact): reward f32[B], flags8 u8[B], solution_cost f32[B],
+        mask_bits i32[B, AW].  unpack_flags8() decodes the flag byte."""
+        B, AW = self.B, self.desc.AW
+        return (torch.zeros(B, dtype=torch.float32).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory(),
+                torch.zeros(B, dtype=torch.float32).pin_memory(), torch.zeros((B, AW), dtype=torch.int32).pin_memory())
+
+    @staticmethod
+    def unpack_flags8(f8):
+        """flags8 -> (done bool, solved int8 in {-1, 0, 1}, status uint8, has_mask bool); include/graphenvs_b200.h: GE_FLAGS8_*."""
+        f = f8.numpy() if isinstance(f8, torch.Tensor) else np.asarray(f8)
+        return (f & 1).astype(bool), (((f >> 1) & 3).astype(np.int8) - 1), ((f >> 3) & 3).astype(np.uint8), ((f >> 5) & 1).astype(bool)
+
     def host_stepper(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None, stream=None, pipelined=False,
-                     chunks=4, obs_x=None):
+                     chunks=4, obs_x=None, compact=False):
         """Zero-argument callable = step_host on FIXED pinned buffers, arguments marshalled once.  On a
         non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph.
         pipelined=True: ge_step_host_pipelined -- the batch is stepped in `chunks` slices on parallel graph branches,
@@ -484,10 +497,12 @@ class BatchedGraphEnv:
         assert obs_x is None or (pipelined and obs_x.is_cuda and obs_x.dtype == torch.float32 and obs_x.is_contiguous()
                                  and obs_x.numel() == self.B * self.N * self.F)
         self.desc.obs_x = obs_x.data_ptr() if obs_x is not None else None
+        if compact:   # flags as one byte per env, solution_cost as float32 (host_io_compact() buffers)
+            assert pipelined and st.cuda_stream != 0 and h_mask is None and h_flags.dtype == torch.uint8 and h_cost.dtype == torch.float32
         if pipelined and st.cuda_stream != 0 and h_mask is None:
             args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
                     _ptr(h_cost), _ptr(h_mask_bits), int(chunks), C.c_void_p(st.cuda_stream))
-            fn = self.lib.ge_step_host_pipelined
+            fn = self.lib.ge_step_host_compact if compact else self.lib.ge_step_host_pipelined
         else:
             args = (C.byref(self.desc), _ptr(h_actions), _ptr(self.actions_dev), C.byref(self._out), _ptr(h_reward), _ptr(h_flags),
                     _ptr(h_cost), _ptr(h_mask), _ptr(h_mask_bits), C.c_void_p(st.cuda_stream))

@@ -889,6 +889,36 @@ __global__ void __launch_bounds__(256) writeback_kernel(const float *reward, con
     if (h_cost) copy_out(h_cost, cost, (size_t)n * 8, tid, nt);
     if (h_mask_bits) copy_out(h_mask_bits, mask_bits, (size_t)n * AW * 4, tid, nt);
 }
+// Compact variant (ge_step_host_compact): flags as ONE byte per env (GE_FLAGS8_*), solution_cost as float32 -- 9 instead of 16
+// bytes per env next to the packed mask.  A thread packs 16 envs' flags into one 16-byte store, 4 envs' costs into another.
+__device__ __forceinline__ uint32_t flags8(const ge_step_flags &f) {
+    return (uint32_t)(f.done & 1u) | ((uint32_t)(f.solved + 1) & 3u) << 1 | ((uint32_t)f.status & 3u) << 3 | ((uint32_t)f.has_mask & 1u) << 5;
+}
+__global__ void __launch_bounds__(256) writeback_compact_kernel(const float *reward, const ge_step_flags *flags, const double *cost,
+                                                              const uint32_t *mask_bits, float *h_reward, uint8_t *h_flags8, float *h_cost32,
+                                                              uint32_t *h_mask_bits, int n, int AW) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    copy_out(h_reward, reward, (size_t)n * 4, tid, nt);
+    for (int g = tid; g < (n >> 4); g += nt) {                       // 16 envs -> 16 bytes
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 f4 = reinterpret_cast<const uint4 *>(flags)[4 * g + q];     // four ge_step_flags
+            const ge_step_flags *f = reinterpret_cast<const ge_step_flags *>(&f4);
+            w[q] = flags8(f[0]) | flags8(f[1]) << 8 | flags8(f[2]) << 16 | flags8(f[3]) << 24;
+        }
+        reinterpret_cast<uint4 *>(h_flags8)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (int b = (n & ~15) + tid; b < n; b += nt) h_flags8[b] = (uint8_t)flags8(flags[b]);
+    if (h_cost32) {
+        for (int g = tid; g < (n >> 2); g += nt) {                   // 4 envs -> 16 bytes
+            const double2 a = reinterpret_cast<const double2 *>(cost)[2 * g], c = reinterpret_cast<const double2 *>(cost)[2 * g + 1];
+            reinterpret_cast<float4 *>(h_cost32)[g] = make_float4((float)a.x, (float)a.y, (float)c.x, (float)c.y);
+        }
+        for (int b = (n & ~3) + tid; b < n; b += nt) h_cost32[b] = (float)cost[b];
+    }
+    if (h_mask_bits) copy_out(h_mask_bits, mask_bits, (size_t)n * AW * 4, tid, nt);
+}
 }  // namespace
 
 // GE_PIPE_ZC (default on): the step kernels of ge_step_host_pipelined read the actions straight from the caller's pinned
@@ -1000,22 +1030,31 @@ static int pipelined_copy_in(const ge_batch *d, int lo, int n, const int32_t *h_
     GE_CUDA_OK(cudaMemcpyAsync(d_actions + lo, h_actions + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     return GE_OK;
 }
+static int g_pipe_pdl = -1;
 static int pipelined_step(const ge_batch *d, int lo, int n, const int32_t *d_actions, const ge_step_out *out, cudaStream_t s) {
     ge_batch sl;
     int rc = ge_batch_slice(d, lo, n, &sl);
     if (rc) return rc;
+    // slices after the first follow another slice's step kernel on this stream (different envs): programmatic dependent launch
+    // lets them become resident under its tail (GE_PIPE_PDL=0 switches it off)
+    if (lo > 0 && env_flag("GE_PIPE_PDL", &g_pipe_pdl, true)) sl.flags |= GE_FLAG_PDL;
     ge_step_out so = {out->reward + lo, out->flags + lo, out->solution_cost + lo};
     return ge_step(&sl, d_actions + lo, &so, (void *)s);
 }
-static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_out *out, float *h_reward, ge_step_flags *h_flags,
-                                double *h_solution_cost, uint32_t *h_mask_bits, cudaStream_t s) {
+static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_out *out, float *h_reward, void *h_flags,
+                                void *h_solution_cost, uint32_t *h_mask_bits, bool compact, cudaStream_t s) {
     const size_t bytes = (size_t)n * (16 + 4 * (size_t)d->AW);
     int blocks = (int)((bytes / 16 + 255) / 256);
     if (blocks > 32) blocks = 32;     // a handful of CTAs saturate PCIe; the rest of the GPU keeps stepping the next slice
     if (blocks < 1) blocks = 1;
-    writeback_kernel<<<blocks, 256, 0, s>>>(out->reward + lo, out->flags + lo, out->solution_cost + lo, d->mask_bits + (size_t)lo * d->AW,
-                                            h_reward + lo, h_flags + lo, h_solution_cost ? h_solution_cost + lo : nullptr,
-                                            h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
+    if (compact)
+        writeback_compact_kernel<<<blocks, 256, 0, s>>>(out->reward + lo, out->flags + lo, out->solution_cost + lo, d->mask_bits + (size_t)lo * d->AW,
+                                                        h_reward + lo, (uint8_t *)h_flags + lo, h_solution_cost ? (float *)h_solution_cost + lo : nullptr,
+                                                        h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
+    else
+        writeback_kernel<<<blocks, 256, 0, s>>>(out->reward + lo, out->flags + lo, out->solution_cost + lo, d->mask_bits + (size_t)lo * d->AW,
+                                                h_reward + lo, (ge_step_flags *)h_flags + lo, h_solution_cost ? (double *)h_solution_cost + lo : nullptr,
+                                                h_mask_bits ? h_mask_bits + (size_t)lo * d->AW : nullptr, n, d->AW);
     GE_CUDA_OK(cudaGetLastError());
     if (d->obs_x) {   // node columns of the slice's observation, on the same lane (runs while the next slice steps)
         int rc = ge_obs_nodes(d, lo, n, d->obs_x + (size_t)lo * (ge_obs_len(d) - (size_t)(is_edge_kind(d->kind) ? 4 : 3) * d->M), (void *)s);
@@ -1024,9 +1063,23 @@ static int pipelined_write_back(const ge_batch *d, int lo, int n, const ge_step_
     return GE_OK;
 }
 
+static int step_host_pipelined_impl(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                                    void *h_flags, void *h_solution_cost, uint32_t *h_mask_bits, int chunks, bool compact, void *stream);
+
 int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                            ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits, int chunks, void *stream) {
     GE_NVTX("ge_step_host_pipelined");
+    return step_host_pipelined_impl(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, chunks, false, stream);
+}
+
+int ge_step_host_compact(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                         uint8_t *h_flags8, float *h_solution_cost32, uint32_t *h_mask_bits, int chunks, void *stream) {
+    GE_NVTX("ge_step_host_compact");
+    return step_host_pipelined_impl(d, h_actions, d_actions, out, h_reward, h_flags8, h_solution_cost32, h_mask_bits, chunks, true, stream);
+}
+
+static int step_host_pipelined_impl(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                                    void *h_flags, void *h_solution_cost, uint32_t *h_mask_bits, int chunks, bool compact, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_batch(d);
     if (rc) return rc;
@@ -1040,7 +1093,7 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
     cudaGraphExec_t exec;
     {
         std::lock_guard<std::mutex> lock(g_hsg_mu);
-        exec = hsg_find(d, key, st, chunks);
+        exec = hsg_find(d, key, st, chunks | (compact ? 0x100 : 0));
     }
     if (!exec) {
         // first call: one direct pass on the caller's stream (sets kernel attributes, does THIS step), then capture the
@@ -1054,7 +1107,7 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
             const int lo = i * per, n = (lo + per <= d->B) ? per : d->B - lo;
             if (!zc && (rc = pipelined_copy_in(d, lo, n, h_actions, d_actions, st))) return rc;
             if ((rc = pipelined_step(d, lo, n, acts, out, st))) return rc;
-            if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, st))) return rc;
+            if ((rc = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, compact, st))) return rc;
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lock(g_hsg_mu);
@@ -1086,13 +1139,13 @@ int ge_step_host_pipelined(const ge_batch *d, const int32_t *h_actions, int32_t 
                 }
                 if (rc2 == GE_OK) rc2 = pipelined_step(d, lo, n, acts, out, st);
                 ok = ok && cudaEventRecord(g_stepped[i], st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_stepped[i], 0) == cudaSuccess;
-                if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, s_out);
+                if (rc2 == GE_OK) rc2 = pipelined_write_back(d, lo, n, out, h_reward, h_flags, h_solution_cost, h_mask_bits, compact, s_out);
             }
             ok = ok && cudaEventRecord(g_join, s_out) == cudaSuccess && cudaStreamWaitEvent(st, g_join, 0) == cudaSuccess;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (ok && rc2 == GE_OK && e == cudaSuccess && graph) {
                 cudaGraphExec_t ex = nullptr;
-                if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) hsg_insert(d, key, st, chunks, ex);
+                if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) hsg_insert(d, key, st, chunks | (compact ? 0x100 : 0), ex);
             }
             if (graph) cudaGraphDestroy(graph);
             (void)cudaGetLastError();

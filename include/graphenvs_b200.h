@@ -284,6 +284,16 @@ int ge_step_host(const ge_batch *batch, const int32_t *h_actions, int32_t *d_act
 int ge_step_host_pipelined(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                            float *h_reward, ge_step_flags *h_flags, double *h_solution_cost, uint32_t *h_mask_bits,
                            int chunks, void *stream);
+/* ge_step_host_pipelined with COMPACT host results: 9 instead of 16 bytes per env next to the packed mask (PCIe write time is what a
+ * host step waits for).  h_flags8[b] = done | (solved + 1) << 1 | status << 3 | has_mask << 5 (GE_FLAGS8_* below); h_solution_cost32 =
+ * (float) solution_cost, NaN = key absent (within the 1e-5 relative tolerance of the parity contract; costs of the fp32 kinds are
+ * float values already).  Same slices, lanes and completion rule. */
+#define GE_FLAGS8_DONE(f) ((f) & 1)
+#define GE_FLAGS8_SOLVED(f) ((int)(((f) >> 1) & 3) - 1)
+#define GE_FLAGS8_STATUS(f) (((f) >> 3) & 3)
+#define GE_FLAGS8_HAS_MASK(f) (((f) >> 5) & 1)
+int ge_step_host_compact(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
+                         float *h_reward, uint8_t *h_flags8, float *h_solution_cost32, uint32_t *h_mask_bits, int chunks, void *stream);
 /* Drops the cached CUDA graphs ge_step_host / ge_step_host_pipelined built for this batch (call before freeing its memory). */
 int ge_step_host_release(const ge_batch *batch);
 

@@ -261,16 +261,21 @@ def test_pipelined_host_step_equals_single_pass(cfg):
     env_id, N, E, kw = cfg
     B, T = 1000, 30
     logs = []
-    for pipelined in (False, True):
+    for mode in ("single", "pipelined", "compact"):
+        pipelined = mode != "single"
         e = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
         e.generate(seed=33)
         e.reset()
-        blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
+        if mode == "compact":    # ge_step_host_compact: one flag byte per env, float32 solution_cost
+            h_rew, h_flg, h_cost, h_bits = e.host_io_compact()
+        else:
+            blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
         h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
         side = torch.cuda.Stream()
         torch.cuda.synchronize()
         xbuf = torch.zeros((B, N, e.F), dtype=torch.float32, device="cuda") if pipelined else None
-        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3, obs_x=xbuf)
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3, obs_x=xbuf,
+                                 compact=(mode == "compact"))
         log = []
         for t in range(T):
             h_act.copy_(e.sample_actions(9, t).cpu())
@@ -279,15 +284,24 @@ def test_pipelined_host_step_equals_single_pass(cfg):
             if pipelined:   # ge_batch.obs_x: the call also rewrote the observation's node columns, slice by slice
                 assert torch.equal(xbuf, e.obs_nodes()), "obs_x must hold the node columns of the state after the step"
             assert torch.equal(h_bits, e.t["mask_bits"].cpu()), "host mask must equal the device mask after the call"
-            assert torch.equal(h_rew, e.reward.cpu()) and torch.equal(h_flg, e.flags.cpu())
-            log.append((h_rew.clone(), h_flg.clone(), h_cost.clone(), h_bits.clone()))
+            assert torch.equal(h_rew, e.reward.cpu())
+            if mode == "compact":
+                done, solved, status, has_mask = BatchedGraphEnv.unpack_flags8(h_flg)
+                flg = torch.from_numpy(np.stack([done.astype(np.uint8), solved.astype(np.int8).view(np.uint8), status, has_mask.astype(np.uint8)], axis=1))
+                assert torch.equal(flg, e.flags.cpu()), "flag byte must decode to the four flag fields"
+                assert torch.equal(torch.nan_to_num(h_cost, nan=-7.0), torch.nan_to_num(e.solution_cost.float().cpu(), nan=-7.0))
+                log.append((h_rew.clone(), flg, e.solution_cost.cpu().clone(), h_bits.clone()))
+            else:
+                assert torch.equal(h_flg, e.flags.cpu())
+                log.append((h_rew.clone(), h_flg.clone(), h_cost.clone(), h_bits.clone()))
         logs.append((log, e.t["traj"].clone(), e.t["acc"].clone()))
         del stepper
-    (l0, t0, a0), (l1, t1, a1) = logs
-    for (r0, f0, c0, m0), (r1, f1, c1, m1) in zip(l0, l1):
-        assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
-        assert torch.equal(torch.nan_to_num(c0, nan=-7.0), torch.nan_to_num(c1, nan=-7.0))
-    assert torch.equal(t0, t1) and torch.equal(a0, a1)
+    (l0, t0, a0) = logs[0]
+    for (l1, t1, a1) in logs[1:]:
+        for (r0, f0, c0, m0), (r1, f1, c1, m1) in zip(l0, l1):
+            assert torch.equal(r0, r1) and torch.equal(f0, f1) and torch.equal(m0, m1)
+            assert torch.equal(torch.nan_to_num(c0, nan=-7.0), torch.nan_to_num(c1, nan=-7.0))
+        assert torch.equal(t0, t1) and torch.equal(a0, a1)
 
 
 def test_sliced_descriptors_step_like_the_full_batch():
