@@ -685,7 +685,11 @@ static int step_impl(const ge_batch *d, int32_t *actions, const ge_step_out *out
     const bool six = d->kind == GE_DISTRIBUTION_CENTER && d->wcode && d->dfa && !getenv("GE_DC_MINB4");
     auto kernel = sampled ? (six ? step_kernel<true, 6> : step_kernel<true, 4>) : (six ? step_kernel<false, 6> : step_kernel<false, 4>);
     if ((rc = set_smem(kernel, smem))) return rc;
-    GE_CUDA_OK(ge_launch_step(kernel, dim3(blocks), dim3(GE_WPB * 32), smem, (cudaStream_t)stream, *d, actions, *out, wpw, seed, t));
+    {
+        cudaError_t e = ge_launch_step(kernel, dim3(blocks), dim3(GE_WPB * 32), smem, (cudaStream_t)stream, *d, actions, *out, wpw, seed, t);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        GE_CUDA_OK(e);
+    }
     return GE_OK;
 }
 

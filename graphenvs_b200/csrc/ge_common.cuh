@@ -46,8 +46,7 @@ inline cudaError_t ge_launch_step(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = ((d.flags & GE_FLAG_PDL) || ge_pdl_env()) ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, d, args...);
-    return e == cudaSuccess ? cudaGetLastError() : e;
+    return cudaLaunchKernelEx(&cfg, kernel, d, args...);   // a failure is also left for cudaGetLastError() (the callers' *_launched() checks)
 }
 
 namespace ge {

@@ -497,6 +497,7 @@ int ge_lane_step(const ge_batch *d, int32_t *actions, const ge_step_out *out, bo
     int rc = lane_prepare(kernel, smem);
     if (rc) return rc;
     cudaError_t e = ge_launch_step(kernel, dim3((d->B + T - 1) / T), dim3(T), smem, st, *d, actions, *out, seed, t);
+    if (e != cudaSuccess) (void)cudaGetLastError();
     return e == cudaSuccess ? GE_OK : ge_set_error(GE_ERR_CUDA, "lane_step_kernel launch: %s", cudaGetErrorString(e));
 }
 
