@@ -493,7 +493,13 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
     per_launch = traffic if traffic else (tr["bytes_per_launch"] * B / tr["envs"] if tr else lib_bytes * B)
     stream = None
     if fused and not args.no_streaming:
-        stream = measure_streaming(D, flush, wl, B, K, W, env, env0, args, per_launch)
+        try:
+            stream = measure_streaming(D, flush, wl, B, K, W, env, env0, args, per_launch)
+        except torch.cuda.OutOfMemoryError:       # the R batches did not fit after all: the isolated protocol stands alone
+            stream = None
+            torch.cuda.empty_cache()
+        if D.reduce([0.0 if stream else 1.0], "max")[0] > 0:   # some rank could not stream: nobody does
+            stream = None
     clocks = sampler.stop(w0, stream["wall"][1] if stream else w1) if sampler is not None else None
     if stream:
         value, ms_per_step, kern_ms_mean, launch_mode, n_launches = envs_all * K / (stream["total_ms"] * 1e-3), stream["ms_per_step"], stream["ms_per_step"], stream["launch"], stream["gpu_launches"]
