@@ -26,8 +26,8 @@ both sides), no flush inside; the steps rotate over R independent resident batch
 3 x L2 (every step finds its batch cold); one step of a batch = C sub-batch launches on C free-running stream chains, launched with
 programmatic dependent launch.  **Isolated protocol** (round 1's, kept beside it): a 256 MiB write + read flushes L2 before every step, each
 step between its own event pair (~6 µs of launch + event overhead inside every pair).  Workloads whose R batches do not fit in HBM (config 4) report
-the isolated protocol only.  `e2e`: the step through `ge_step_host_pipelined` with pinned host buffers (actions in; reward / flags /
-solution_cost / packed mask out; two slices, the write-back of one overlapping the kernel of the next); `e2e + obs`: the same call also rewrites
+the isolated protocol only.  `e2e`: the step through `ge_step_host_compact` with pinned host buffers (actions in; reward / one flag byte /
+float32 solution_cost / packed mask out; two slices, the write-back of one overlapping the kernel of the next; L2 flushed before every call); `e2e + obs`: the same call also rewrites
 the observation's node columns `x[B, N, F]` on the device (`ge_batch.obs_x`).  CPU port: `oracle/graphenvs_oracle.c` with OpenMP over envs on
 the GPU box's host threads.  Python reference: the unmodified `graph_envs` loop as recorded on the build container
 (`profiles/r02_python_reference_cpu.json`).
