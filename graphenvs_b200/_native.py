@@ -86,7 +86,7 @@ class GeBatch(C.Structure):
         ("src", _P), ("dest", _P), ("target_bits", _P), ("node_cost", _P), ("node_xy", _P),
         ("max_dist32", _P), ("targets", _P), ("in_range", _P), ("in_range_t", _P), ("heuristic", _P), ("heuristic_alt", _P), ("features", _P),
         ("head", _P), ("node_bits", _P), ("node_bits2", _P), ("edge_bits", _P), ("dist32", _P), ("bestkey", _P),
-        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_cnt", _P), ("mask_bytes", _P), ("mask_mirror", _P), ("mask0_bits", _P), ("acc", _P), ("traj", _P), ("env_steps", _P), ("obs_x", _P), ("dc_rows", _P),
+        ("cost", _P), ("counters", _P), ("done", _P), ("mask_bits", _P), ("mask_cnt", _P), ("mask_bytes", _P), ("mask_mirror", _P), ("mask0_bits", _P), ("acc", _P), ("traj", _P), ("env_steps", _P), ("obs_x", _P), ("dc_rows", _P), ("progress", _P),
     ]
 
 
@@ -96,7 +96,7 @@ class StepOut(C.Structure):
 
 EXPORTS = ["ge_abi_version", "ge_last_error", "ge_fill_layout", "ge_step_smem_bytes", "ge_build_adjacency",
            "ge_prepare", "ge_features", "ge_generate", "ge_generate_fallbacks", "ge_pool_refill", "ge_reset", "ge_step", "ge_step_sampled", "ge_sample_actions", "ge_obs_len",
-           "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined", "ge_step_host_compact",
+           "ge_obs_flat", "ge_obs_graph", "ge_obs_nodes", "ge_step_kernel_name", "ge_batch_slice", "ge_step_host", "ge_step_host_pipelined", "ge_step_host_compact", "ge_progress_supported",
            "ge_step_host_release", "ge_mask_mirror_supported", "ge_mask_bytes_current", "ge_mask_bytes", "ge_stats"]
 
 _lib = None

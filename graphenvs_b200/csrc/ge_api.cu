@@ -761,6 +761,8 @@ int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *strea
 
 int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }   // (a sampler / obs call never mirrors)
 
+int ge_progress_supported(const ge_batch *d) { return d && d->kind != GE_PERISHABLE_DELIVERY && ge_lane_eligible(d); }
+
 int ge_mask_bytes_current(const ge_batch *d) { return d && d->mask_bytes && !ge_incr_eligible(d); }
 
 int ge_mask_bytes(const ge_batch *d, int env_lo, int count, void *stream) {
@@ -840,8 +842,11 @@ struct HostStepGraph {
     int chunks;
     cudaGraphExec_t exec;
     bool valid;
+    uint32_t *progress;      // streamed write-back (chunks code 0x200): device counters, one per 1024 envs ...
+    uint32_t *err;           // ... and the writer's give-up flag in mapped host memory
 };
 HostStepGraph g_hsg[HSG_SLOTS];
+bool g_streamed_off = false;                             // set when a streamed write-back ever timed out: sliced path from then on
 int g_hsg_next = 0;
 std::mutex g_hsg_mu;
 cudaStream_t g_side[2];                                  // copy-in lane, write-back lane (the kernels stay on the caller's stream)
@@ -854,13 +859,28 @@ cudaGraphExec_t hsg_find(const ge_batch *d, const void *const *key, cudaStream_t
             return g.exec;
     return nullptr;
 }
-void hsg_insert(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks, cudaGraphExec_t exec) {
+void hsg_drop(HostStepGraph &g) {
+    if (!g.valid) return;
+    cudaGraphExecDestroy(g.exec);
+    if (g.progress) cudaFree(g.progress);
+    if (g.err) cudaFreeHost(g.err);
+    g.progress = g.err = nullptr;
+    g.valid = false;
+}
+HostStepGraph *hsg_entry(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks) {
+    for (HostStepGraph &g : g_hsg)
+        if (g.valid && g.st == st && g.chunks == chunks && memcmp(&g.d, d, sizeof(ge_batch)) == 0 && memcmp(g.p, key, sizeof(g.p)) == 0)
+            return &g;
+    return nullptr;
+}
+void hsg_insert(const ge_batch *d, const void *const *key, cudaStream_t st, int chunks, cudaGraphExec_t exec, uint32_t *progress = nullptr,
+                uint32_t *err = nullptr) {
     HostStepGraph &g = g_hsg[g_hsg_next];
     g_hsg_next = (g_hsg_next + 1) % HSG_SLOTS;
-    if (g.valid) { cudaGraphExecDestroy(g.exec); g.valid = false; }
+    hsg_drop(g);
     memcpy(&g.d, d, sizeof(ge_batch));
     memcpy(g.p, key, sizeof(g.p));
-    g.st = st; g.chunks = chunks; g.exec = exec; g.valid = true;
+    g.st = st; g.chunks = chunks; g.exec = exec; g.valid = true; g.progress = progress; g.err = err;
 }
 
 // Waits for the stream by polling: a blocking synchronize parks the thread and pays the wake-up latency of an
@@ -923,6 +943,70 @@ __global__ void __launch_bounds__(256) writeback_compact_kernel(const float *rew
     }
     if (h_mask_bits) copy_out(h_mask_bits, mask_bits, (size_t)n * AW * 4, tid, nt);
 }
+
+// Streamed write-back (ge_step_host_pipelined, chunks = 0): runs CONCURRENTLY with the one step kernel of the call.  Block j
+// waits for chunk c = j, j + gridDim, ... of 1024 envs to be complete (ge_batch.progress, written by the step kernel with
+// release semantics), then moves that chunk's results into the pinned host arrays: results cross PCIe while later chunks are
+// still being stepped, and the call ends one chunk's transfer after the step kernel instead of a whole slice's.  The wait is
+// BOUNDED (it gives up and raises *err; the host then falls back to the sliced path), so a scheduler that serialised the two
+// kernels the wrong way round cannot hang the GPU.  Loads bypass L1 (the data was written by other SMs during this kernel).
+__device__ __forceinline__ void copy_out_cg(void *dst, const void *src, size_t bytes, int tid, int nthreads) {
+    const size_t n16 = bytes >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (size_t i = tid; i < n16; i += nthreads) d4[i] = __ldcg(s4 + i);
+    for (size_t i = (n16 << 4) + tid; i < bytes; i += nthreads) reinterpret_cast<unsigned char *>(dst)[i] = __ldcg(reinterpret_cast<const unsigned char *>(src) + i);
+}
+__global__ void __launch_bounds__(256) writeback_stream_kernel(uint32_t *progress, int n_chunks, int B, const float *reward, const ge_step_flags *flags,
+                                                             const double *cost, const uint32_t *mask_bits, float *h_reward, void *h_flags, void *h_cost,
+                                                             uint32_t *h_mask_bits, int AW, int compact, volatile uint32_t *err) {
+    __shared__ int ok;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int lo = c << GE_PROGRESS_SHIFT, n = min(1 << GE_PROGRESS_SHIFT, B - lo);
+        if (tid == 0) {
+            unsigned spins = 0, seen;
+            ok = 1;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + c) : "memory");
+                if (seen >= (unsigned)n) break;
+                if (++spins > (1u << 21)) { ok = 0; break; }          // ~0.2 s: give up, never hang
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (!ok) { if (tid == 0) *err = 1u; return; }
+        copy_out_cg(h_reward + lo, reward + lo, (size_t)n * 4, tid, nt);
+        if (compact) {
+            uint8_t *hf = reinterpret_cast<uint8_t *>(h_flags) + lo;
+            for (int g = tid; g < (n >> 4); g += nt) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 f4 = __ldcg(reinterpret_cast<const uint4 *>(flags + lo) + 4 * g + q);
+                    const ge_step_flags *f = reinterpret_cast<const ge_step_flags *>(&f4);
+                    w[q] = flags8(f[0]) | flags8(f[1]) << 8 | flags8(f[2]) << 16 | flags8(f[3]) << 24;
+                }
+                reinterpret_cast<uint4 *>(hf)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            for (int b = (n & ~15) + tid; b < n; b += nt) { const uint32_t f1 = __ldcg(reinterpret_cast<const uint32_t *>(flags + lo) + b); hf[b] = (uint8_t)flags8(*reinterpret_cast<const ge_step_flags *>(&f1)); }
+            if (h_cost) {
+                float *hc = reinterpret_cast<float *>(h_cost) + lo;
+                for (int g = tid; g < (n >> 2); g += nt) {
+                    const double2 a = __ldcg(reinterpret_cast<const double2 *>(cost + lo) + 2 * g), cc = __ldcg(reinterpret_cast<const double2 *>(cost + lo) + 2 * g + 1);
+                    reinterpret_cast<float4 *>(hc)[g] = make_float4((float)a.x, (float)a.y, (float)cc.x, (float)cc.y);
+                }
+                for (int b = (n & ~3) + tid; b < n; b += nt) hc[b] = (float)__ldcg(cost + lo + b);
+            }
+        } else {
+            copy_out_cg(reinterpret_cast<ge_step_flags *>(h_flags) + lo, flags + lo, (size_t)n * 4, tid, nt);
+            if (h_cost) copy_out_cg(reinterpret_cast<double *>(h_cost) + lo, cost + lo, (size_t)n * 8, tid, nt);
+        }
+        if (h_mask_bits) copy_out_cg(h_mask_bits + (size_t)lo * AW, mask_bits + (size_t)lo * AW, (size_t)n * AW * 4, tid, nt);
+        __syncthreads();
+        if (tid == 0) progress[c] = 0;                                 // consumed: re-armed for the next replay
+    }
+}
 }  // namespace
 
 // GE_PIPE_ZC (default on): the step kernels of ge_step_host_pipelined read the actions straight from the caller's pinned
@@ -961,7 +1045,7 @@ int ge_step_host_release(const ge_batch *d) {
     if (!d) return GE_OK;
     std::lock_guard<std::mutex> lock(g_hsg_mu);
     for (HostStepGraph &g : g_hsg)
-        if (g.valid && g.d.mask_bits == d->mask_bits) { cudaGraphExecDestroy(g.exec); g.valid = false; }
+        if (g.valid && g.d.mask_bits == d->mask_bits) hsg_drop(g);
     return GE_OK;
 }
 
@@ -1082,6 +1166,82 @@ int ge_step_host_compact(const ge_batch *d, const int32_t *h_actions, int32_t *d
     return step_host_pipelined_impl(d, h_actions, d_actions, out, h_reward, h_flags8, h_solution_cost32, h_mask_bits, chunks, true, stream);
 }
 
+static int ensure_side_streams() {   // (g_hsg_mu held)
+    if (g_side_ready) return GE_OK;
+    for (int i = 0; i < 2; ++i) GE_CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < HSG_MAX_CHUNKS; ++i) {
+        GE_CUDA_OK(cudaEventCreateWithFlags(&g_in[i], cudaEventDisableTiming));
+        GE_CUDA_OK(cudaEventCreateWithFlags(&g_stepped[i], cudaEventDisableTiming));
+    }
+    GE_CUDA_OK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    GE_CUDA_OK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+    g_side_ready = true;
+    return GE_OK;
+}
+
+// chunks = 0: one full-batch step kernel that signals ge_batch.progress + the concurrent writer.  Zero-copy action reads.
+static int step_host_streamed(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
+                              void *h_flags, void *h_solution_cost, uint32_t *h_mask_bits, bool compact, cudaStream_t st) {
+    const void *key[10] = {h_actions, d_actions, out->reward, out->flags, out->solution_cost, h_reward, h_flags, h_solution_cost, nullptr, h_mask_bits};
+    const int code = 0x200 | (compact ? 0x100 : 0);
+    const int n_chunks = (d->B + (1 << GE_PROGRESS_SHIFT) - 1) >> GE_PROGRESS_SHIFT;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t *progress = nullptr, *err = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_hsg_mu);
+        if (HostStepGraph *g = hsg_entry(d, key, st, code)) { exec = g->exec; progress = g->progress; err = g->err; }
+    }
+    int rc;
+    if (exec) {
+        GE_CUDA_OK(cudaGraphLaunch(exec, st));
+        GE_CUDA_OK(spin_until_done(st));
+        if (*reinterpret_cast<volatile uint32_t *>(err)) {
+            // the writer gave up (the two kernels did not run concurrently): the step itself is done; deliver its results with a
+            // plain write-back, re-arm the counters and use the sliced path from now on
+            *err = 0;
+            g_streamed_off = true;
+            GE_CUDA_OK(cudaMemsetAsync(progress, 0, sizeof(uint32_t) * n_chunks, st));
+            if ((rc = pipelined_write_back(d, 0, d->B, out, h_reward, h_flags, h_solution_cost, h_mask_bits, compact, st))) return rc;
+            GE_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return GE_OK;
+    }
+    // first call: this step through one plain pass, then capture the two-branch graph for the following calls
+    if ((rc = pipelined_step(d, 0, d->B, h_actions, out, st))) return rc;
+    if ((rc = pipelined_write_back(d, 0, d->B, out, h_reward, h_flags, h_solution_cost, h_mask_bits, compact, st))) return rc;
+    GE_CUDA_OK(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lock(g_hsg_mu);
+    if ((rc = ensure_side_streams())) return rc;
+    GE_CUDA_OK(cudaMalloc(&progress, sizeof(uint32_t) * n_chunks));
+    GE_CUDA_OK(cudaMemset(progress, 0, sizeof(uint32_t) * n_chunks));
+    GE_CUDA_OK(cudaHostAlloc(&err, sizeof(uint32_t), cudaHostAllocMapped));
+    *err = 0;
+    cudaGraph_t graph = nullptr;
+    bool inserted = false;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        cudaStream_t s_out = g_side[1];
+        bool ok = cudaEventRecord(g_fork, st) == cudaSuccess && cudaStreamWaitEvent(s_out, g_fork, 0) == cudaSuccess;
+        int nb = n_chunks < 32 ? n_chunks : 32;
+        writeback_stream_kernel<<<nb, 256, 0, s_out>>>(progress, n_chunks, d->B, out->reward, out->flags, out->solution_cost, d->mask_bits, h_reward,
+                                                       h_flags, h_solution_cost, h_mask_bits, d->AW, compact ? 1 : 0, err);
+        ok = ok && cudaGetLastError() == cudaSuccess;
+        ge_batch dd = *d;
+        dd.progress = progress;
+        int rc2 = ge_step(&dd, h_actions, out, (void *)st);
+        if (rc2 == GE_OK && d->obs_x) rc2 = ge_obs_nodes(d, 0, d->B, d->obs_x, (void *)st);
+        ok = ok && cudaEventRecord(g_join, s_out) == cudaSuccess && cudaStreamWaitEvent(st, g_join, 0) == cudaSuccess;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (ok && rc2 == GE_OK && e == cudaSuccess && graph) {
+            cudaGraphExec_t ex = nullptr;
+            if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) { hsg_insert(d, key, st, code, ex, progress, err); inserted = true; }
+        }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    (void)cudaGetLastError();
+    if (!inserted) { cudaFree(progress); cudaFreeHost(err); g_streamed_off = true; }
+    return GE_OK;
+}
+
 static int step_host_pipelined_impl(const ge_batch *d, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out, float *h_reward,
                                     void *h_flags, void *h_solution_cost, uint32_t *h_mask_bits, int chunks, bool compact, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -1089,7 +1249,13 @@ static int step_host_pipelined_impl(const ge_batch *d, const int32_t *h_actions,
     if (rc) return rc;
     if (!h_actions || !d_actions || !out || !h_reward || !h_flags) return fail(GE_ERR_ARG, "null step buffers");
     if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return fail(GE_ERR_ARG, "ge_step_host_pipelined needs a created (capturable) stream");
-    if (chunks < 1) chunks = 1;
+    if (chunks <= 0) {   // streamed write-back: ONE step kernel + a concurrent writer fed by ge_batch.progress (see writeback_stream_kernel)
+        static int off = -1;
+        if (off < 0) off = getenv("GE_NO_STREAMED") ? 1 : 0;
+        if (!off && !g_streamed_off && ge_progress_supported(d) && env_flag("GE_PIPE_ZC", &g_pipe_zc, true))
+            return step_host_streamed(d, h_actions, d_actions, out, h_reward, h_flags, h_solution_cost, h_mask_bits, compact, st);
+        chunks = 2;      // kernel family without progress counters: two slices
+    }
     if (chunks > HSG_MAX_CHUNKS) chunks = HSG_MAX_CHUNKS;
     int per = ((d->B + chunks - 1) / chunks + 127) & ~127;    // slice starts are multiples of 128 envs (tiles, vector alignment)
     chunks = (d->B + per - 1) / per;
@@ -1115,16 +1281,7 @@ static int step_host_pipelined_impl(const ge_batch *d, const int32_t *h_actions,
         }
         GE_CUDA_OK(cudaStreamSynchronize(st));
         std::lock_guard<std::mutex> lock(g_hsg_mu);
-        if (!g_side_ready) {
-            for (int i = 0; i < 2; ++i) GE_CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
-            for (int i = 0; i < HSG_MAX_CHUNKS; ++i) {
-                GE_CUDA_OK(cudaEventCreateWithFlags(&g_in[i], cudaEventDisableTiming));
-                GE_CUDA_OK(cudaEventCreateWithFlags(&g_stepped[i], cudaEventDisableTiming));
-            }
-            GE_CUDA_OK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-            GE_CUDA_OK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-            g_side_ready = true;
-        }
+        if ((rc = ensure_side_streams())) return rc;
         // Three lanes: copy-in chain (g_side[0]) -> step-kernel chain (caller's stream) -> write-back chain (g_side[1]).
         // The kernels of the slices run ONE AFTER THE OTHER: launched side by side they would share the GPU, finish
         // together, and every write-back would start as late as after a single big kernel (measured: no gain).  Chained,

@@ -53,6 +53,19 @@ namespace ge {
 
 typedef unsigned long long u64;
 
+// ge_batch.progress: the threads of a warp that have finished their envs (one env per thread, same 1024-env chunk: chunks are
+// tile-aligned) publish them together -- group barrier, then ONE release (fence + atomic) by the group's first thread, which by
+// cumulativity covers the stores of the whole group.  Whatever subset of the warp arrives here together forms a group.
+#define GE_PROGRESS_SHIFT 10
+__device__ __forceinline__ void signal_progress(const ge_batch &d, int b) {
+    const unsigned m = __activemask();
+    __syncwarp(m);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+        __threadfence();
+        atomicAdd(d.progress + (b >> GE_PROGRESS_SHIFT), (unsigned)__popc(m));
+    }
+}
+
 // griddepcontrol (sm_90+): no-ops when the kernel was not launched as a programmatic dependent.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

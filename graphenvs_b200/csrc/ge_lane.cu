@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(GE_LANE_T) lane_step_kernel(ge_batch d, int32_
         if (done) d.done[b] = 1;
         lane_store_state(d, b, s, mask, kind == GE_DENSEST_SUBGRAPH);
     }
+    if (d.progress) signal_progress(d, b);   // streamed host step: this env's results may cross PCIe now
 }
 
 template <bool STAGED>

@@ -188,6 +188,10 @@ typedef struct ge_batch {
                                               0xffffffff.  The cutoff search then needs no row_ptr lookup (one dependent memory round
                                               less per search level), reads sector-aligned rows, and prefetches a row when its node is
                                               queued; a prefix longer than 32 entries continues in dc_edges */
+    uint32_t *progress;           /* [ceil(B / 1024)] optional DEVICE counters, or NULL: a step kernel that supports it (ge_progress_supported)
+                                              adds the number of envs it has finished -- every store of those envs made visible first -- to
+                                              progress[env >> 10].  ge_step_host_pipelined with chunks = 0 uses it to stream results to the host
+                                              from a concurrent write-back kernel while the step kernel is still running */
 } ge_batch;
 
 /* step outputs (device pointers) */
@@ -294,6 +298,8 @@ int ge_step_host_pipelined(const ge_batch *batch, const int32_t *h_actions, int3
 #define GE_FLAGS8_HAS_MASK(f) (((f) >> 5) & 1)
 int ge_step_host_compact(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                          float *h_reward, uint8_t *h_flags8, float *h_solution_cost32, uint32_t *h_mask_bits, int chunks, void *stream);
+/* 1 when the step kernel this batch dispatches to signals ge_batch.progress (the lane-per-env families). */
+int ge_progress_supported(const ge_batch *batch);
 /* Drops the cached CUDA graphs ge_step_host / ge_step_host_pipelined built for this batch (call before freeing its memory). */
 int ge_step_host_release(const ge_batch *batch);
 

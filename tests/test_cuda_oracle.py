@@ -261,11 +261,13 @@ def test_pipelined_host_step_equals_single_pass(cfg):
     env_id, N, E, kw = cfg
     B, T = 1000, 30
     logs = []
-    for mode in ("single", "pipelined", "compact"):
+    for mode in ("single", "pipelined", "compact", "streamed"):
         pipelined = mode != "single"
         e = BatchedGraphEnv(env_id, B, N, E, auto_reset=True, **kw)
         e.generate(seed=33)
         e.reset()
+        if mode == "streamed":   # chunks = 0: one step kernel + the concurrent write-back fed by ge_batch.progress (lane families; two slices elsewhere)
+            assert bool(e.lib.ge_progress_supported(__import__("ctypes").byref(e.desc))) == (env_id == "LongestPath-v0")
         if mode == "compact":    # ge_step_host_compact: one flag byte per env, float32 solution_cost
             h_rew, h_flg, h_cost, h_bits = e.host_io_compact()
         else:
@@ -274,8 +276,8 @@ def test_pipelined_host_step_equals_single_pass(cfg):
         side = torch.cuda.Stream()
         torch.cuda.synchronize()
         xbuf = torch.zeros((B, N, e.F), dtype=torch.float32, device="cuda") if pipelined else None
-        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=3, obs_x=xbuf,
-                                 compact=(mode == "compact"))
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=pipelined, chunks=0 if mode == "streamed" else 3,
+                                 obs_x=xbuf, compact=(mode == "compact"))
         log = []
         for t in range(T):
             h_act.copy_(e.sample_actions(9, t).cpu())

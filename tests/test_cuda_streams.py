@@ -83,3 +83,34 @@ def test_pdl_chain_on_one_stream_equals_plain():
     for k in STATE:
         if k in ref.t:
             assert torch.equal(ref.t[k], env.t[k]), k
+
+
+@pytest.mark.parametrize("compact", [False, True], ids=["full", "compact"])
+def test_streamed_host_step_equals_sliced(compact):
+    """ge_step_host_pipelined / _compact with chunks = 0 (one step kernel signalling ge_batch.progress + a concurrent write-back kernel
+    that ships every 1024-env chunk as soon as it is complete) delivers exactly what the two-slice path delivers; 20 chunks, ragged tail."""
+    cfg = ("LongestPath-v0", 50, 200, {"parenting": 2}, 20 * 1024 - 200)
+    logs = []
+    for chunks in (2, 0):
+        e = _make(cfg)
+        B = e.B
+        if compact:
+            h_rew, h_flg, h_cost, h_bits = e.host_io_compact()
+        else:
+            _blk, h_rew, h_flg, h_cost, h_bits = e.host_io()
+        h_act = torch.zeros(B, dtype=torch.int32).pin_memory()
+        side = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        stepper = e.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True, chunks=chunks, compact=compact)
+        log = []
+        for t in range(T):
+            h_act.copy_(e.sample_actions(9, t).cpu())
+            torch.cuda.synchronize()
+            stepper()
+            assert torch.equal(h_bits, e.t["mask_bits"].cpu()) and torch.equal(h_rew, e.reward.cpu())
+            log.append((h_rew.clone(), h_flg.clone(), torch.nan_to_num(h_cost.clone(), nan=-7.0), h_bits.clone()))
+        logs.append((log, e.t["traj"].clone()))
+        del stepper
+    for a, b in zip(logs[0][0], logs[1][0]):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert torch.equal(logs[0][1], logs[1][1])
