@@ -1212,9 +1212,13 @@ static int step_host_streamed(const ge_batch *d, const int32_t *h_actions, int32
     GE_CUDA_OK(cudaStreamSynchronize(st));
     std::lock_guard<std::mutex> lock(g_hsg_mu);
     if ((rc = ensure_side_streams())) return rc;
-    GE_CUDA_OK(cudaMalloc(&progress, sizeof(uint32_t) * n_chunks));
-    GE_CUDA_OK(cudaMemset(progress, 0, sizeof(uint32_t) * n_chunks));
-    GE_CUDA_OK(cudaHostAlloc(&err, sizeof(uint32_t), cudaHostAllocMapped));
+    if (cudaMalloc(&progress, sizeof(uint32_t) * n_chunks) != cudaSuccess || cudaMemset(progress, 0, sizeof(uint32_t) * n_chunks) != cudaSuccess ||
+        cudaHostAlloc(&err, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) {
+        if (progress) cudaFree(progress);
+        (void)cudaGetLastError();
+        g_streamed_off = true;           // this step is done; later calls take the sliced path
+        return GE_OK;
+    }
     *err = 0;
     cudaGraph_t graph = nullptr;
     bool inserted = false;

@@ -116,3 +116,18 @@ def test_registry_ids():
         registration.make("NoSuchEnv-v0", n_nodes=5, n_edges=6)
     with pytest.raises(AssertionError):                                   # perishable_product_delivery.py:29
         spec.check_ctor_args("PerishableProductDelivery-v0", 10, 20, {"parenting": 2})
+
+
+def test_flags8_decoding_matches_the_header_macros():
+    """BatchedGraphEnv.unpack_flags8 (compact host results, ge_step_host_compact) = GE_FLAGS8_* of include/graphenvs_b200.h."""
+    import numpy as np
+    from graphenvs_b200.batch import BatchedGraphEnv
+    cases = [(d, s, st, h) for d in (0, 1) for s in (-1, 0, 1) for st in (0, 1, 2) for h in (0, 1)]
+    f8 = np.array([d | (s + 1) << 1 | st << 3 | h << 5 for d, s, st, h in cases], dtype=np.uint8)
+    done, solved, status, has_mask = BatchedGraphEnv.unpack_flags8(f8)
+    for i, (d, s, st, h) in enumerate(cases):
+        assert (int(done[i]), int(solved[i]), int(status[i]), int(has_mask[i])) == (d, s, st, h)
+    hdr = open(os.path.join(ROOT, "include", "graphenvs_b200.h")).read()
+    for macro in ("GE_FLAGS8_DONE(f) ((f) & 1)", "GE_FLAGS8_SOLVED(f) ((int)(((f) >> 1) & 3) - 1)", "GE_FLAGS8_STATUS(f) (((f) >> 3) & 3)",
+                  "GE_FLAGS8_HAS_MASK(f) (((f) >> 5) & 1)"):
+        assert macro in hdr
