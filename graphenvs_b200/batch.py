@@ -490,8 +490,12 @@ class BatchedGraphEnv:
         """Zero-argument callable = step_host on FIXED pinned buffers, arguments marshalled once.  On a
         non-default stream the C side replays the whole copy-in / step / copy-out sequence as one CUDA graph.
         pipelined=True: ge_step_host_pipelined -- the batch is stepped in `chunks` slices on parallel graph branches,
-        slice i's results cross PCIe while slice i+1 steps (needs a created stream; the byte mask is not returned)."""
+        slice i's results cross PCIe while slice i+1 steps (needs a created stream; the byte mask is not returned).  chunks=0: ONE step
+        kernel + a concurrent write-back kernel fed by per-1024-env progress counters (multi-wave batches: 387 vs 486 us per host step at
+        1M cfg2 envs; no gain for one-wave batches); chunks=None picks between the two."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if chunks is None:   # auto: multi-wave batches of the lane-per-env families stream their results (chunks = 0), the rest use two slices
+            chunks = 0 if (self.B >= 262144 and self.lib.ge_progress_supported(C.byref(self.desc))) else 2
         # obs_x: float32[B, N, F] on the device -- the pipelined step also rewrites the observation's node columns, slice by
         # slice on its write-back lane (ge_batch.obs_x); None switches that off again
         assert obs_x is None or (pipelined and obs_x.is_cuda and obs_x.dtype == torch.float32 and obs_x.is_contiguous()
