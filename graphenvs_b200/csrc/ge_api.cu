@@ -278,7 +278,47 @@ __global__ void __launch_bounds__(256) obs_kernel(ge_batch d, int env_lo, int co
     const bool seeded = kind == GE_SHORTEST_PATH || kind == GE_LONGEST_PATH;
     const int src = seeded ? d.src[b] : 0, dest = seeded ? d.dest[b] : 0;
     const float maxd = (kind == GE_MULTICAST_ROUTING || kind == GE_PERISHABLE_DELIVERY) ? d.max_dist32[b] : 0.f;
-    {   // node section: element i = (v, c) with v = i / F; the pair advances by (blockDim / F, blockDim % F) per trip
+    if (!warp_per_env) {
+        // CTA per env (large graphs): one THREAD per node evaluates the node's F columns once -- the membership bits and the kind
+        // dispatch are per node, not per element (the per-element form was instruction-bound: 2.1 ms for DistributionCenter's
+        // 2.6 GB of x at config 5) -- into a shared tile, which the block then streams out coalesced.
+        __shared__ float tile[256 * 21];
+        for (int v0 = 0; v0 < N; v0 += 256) {
+            const int v = v0 + (int)threadIdx.x;
+            if (v < N) {
+                float *t = tile + (int)threadIdx.x * F;
+                const bool bit = (vis[v >> 5] >> (v & 31)) & 1u;
+                const bool tb = tgt ? ((tgt[v >> 5] >> (v & 31)) & 1u) : false;
+                switch (kind) {
+                case GE_SHORTEST_PATH: t[0] = (float)bit; t[1] = (float)(v == dest); break;
+                case GE_LONGEST_PATH: t[0] = (float)bit; t[1] = (v == dest) ? 1.f : ((d.parenting == 0 && v == src) ? 2.f : 0.f); break;
+                case GE_STEINER_TREE: t[0] = (float)bit; t[1] = (float)tb; break;
+                case GE_TSP:
+                    t[0] = (float)bit; t[1] = (float)(v == 0);
+                    t[2] = d.node_xy ? d.node_xy[((size_t)b * N + v) * 2] : 0.f;
+                    t[3] = d.node_xy ? d.node_xy[((size_t)b * N + v) * 2 + 1] : 0.f;
+                    break;
+                case GE_MAX_INDEPENDENT_SET: t[0] = d.node_cost[(size_t)b * N + v]; t[1] = (float)bit; break;
+                case GE_DENSEST_SUBGRAPH: t[0] = (float)bit; break;
+                case GE_MULTICAST_ROUTING: t[0] = (float)bit; t[1] = (float)tb; t[2] = maxd; t[3] = d.dist32[(size_t)b * N + v]; break;
+                case GE_DISTRIBUTION_CENTER:
+                    t[0] = d.node_cost[(size_t)b * N + v]; t[1] = (float)bit; t[2] = (float)tb;
+                    t[3] = (float)((aux[v >> 5] >> (v & 31)) & 1u); t[4] = (float)d.max_distance;
+                    break;
+                default:   // PerishableProductDelivery: 16 columns through the per-element rule
+                    for (int c = 0; c < dyn; ++c) t[c] = node_value(d, b, v, c, dyn, vis, aux, tgt, src, dest, maxd);
+                }
+                const float *f5 = d.features ? d.features + ((size_t)b * N + v) * 5 : nullptr;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) t[dyn + c] = f5 ? f5[c] : 0.f;
+            }
+            __syncthreads();
+            const int nvals = min(256, N - v0) * F;
+            float *ov = o + (size_t)v0 * F;
+            for (int i = threadIdx.x; i < nvals; i += 256) ov[i] = tile[i];
+            __syncthreads();
+        }
+    } else {   // node section, warp per env: element i = (v, c) with v = i / F; the pair advances by (32 / F, 32 % F) per trip
         int v = gt / F, c = gt - v * F;
         const int dv = gn / F, dc = gn - dv * F;
         for (int i = gt; i < NF; i += gn) {
@@ -761,7 +801,10 @@ int ge_obs_nodes(const ge_batch *d, int env_lo, int count, float *x, void *strea
 
 int ge_mask_mirror_supported(const ge_batch *d) { return d && !ge_incr_eligible(d); }   // (a sampler / obs call never mirrors)
 
-int ge_progress_supported(const ge_batch *d) { return d && d->kind != GE_PERISHABLE_DELIVERY && ge_lane_eligible(d); }
+int ge_progress_supported(const ge_batch *d) {
+    if (!d || d->kind == GE_PERISHABLE_DELIVERY) return 0;
+    return ge_lane_eligible(d) || ge_dc_eligible(d);
+}
 
 int ge_mask_bytes_current(const ge_batch *d) { return d && d->mask_bytes && !ge_incr_eligible(d); }
 

@@ -410,17 +410,21 @@ __global__ void __launch_bounds__(GE_WPB * 32, 6) dc_step_kernel(ge_batch d, int
     if (auto_reset) {                                                            // tail of reset()
         takenw = 0; covw = 0; cost = 0.0;
         maskw = d.mask0_bits ? m0 : dc_reset_mask(d, b, lane, tail, s.cur);
-    } else if (!write_state) {
-        return;
     }
-    if (WL) {
-        d.node_bits[(size_t)b * NW + lane] = takenw;
-        d.node_bits2[(size_t)b * NW + lane] = covw;
+    if (auto_reset || write_state) {
+        if (WL) {
+            d.node_bits[(size_t)b * NW + lane] = takenw;
+            d.node_bits2[(size_t)b * NW + lane] = covw;
+        }
+        dc_store_mask(d, b, lane, maskw);
+        if (lane == 0) {
+            d.cost[b] = cost;
+            if (done && !auto_reset) d.done[b] = 1;
+        }
     }
-    dc_store_mask(d, b, lane, maskw);
-    if (lane == 0) {
-        d.cost[b] = cost;
-        if (done && !auto_reset) d.done[b] = 1;
+    if (d.progress) {   // streamed host step: the whole warp's stores of this env are ordered before one release by lane 0
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicAdd(d.progress + (b >> GE_PROGRESS_SHIFT), 1u); }
     }
 }
 

@@ -298,7 +298,7 @@ int ge_step_host_pipelined(const ge_batch *batch, const int32_t *h_actions, int3
 #define GE_FLAGS8_HAS_MASK(f) (((f) >> 5) & 1)
 int ge_step_host_compact(const ge_batch *batch, const int32_t *h_actions, int32_t *d_actions, const ge_step_out *out,
                          float *h_reward, uint8_t *h_flags8, float *h_solution_cost32, uint32_t *h_mask_bits, int chunks, void *stream);
-/* 1 when the step kernel this batch dispatches to signals ge_batch.progress (the lane-per-env families). */
+/* 1 when the step kernel this batch dispatches to signals ge_batch.progress (the lane-per-env families, DistributionCenter). */
 int ge_progress_supported(const ge_batch *batch);
 /* Drops the cached CUDA graphs ge_step_host / ge_step_host_pipelined built for this batch (call before freeing its memory). */
 int ge_step_host_release(const ge_batch *batch);

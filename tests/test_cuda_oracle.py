@@ -267,7 +267,7 @@ def test_pipelined_host_step_equals_single_pass(cfg):
         e.generate(seed=33)
         e.reset()
         if mode == "streamed":   # chunks = 0: one step kernel + the concurrent write-back fed by ge_batch.progress (lane families; two slices elsewhere)
-            assert bool(e.lib.ge_progress_supported(__import__("ctypes").byref(e.desc))) == (env_id == "LongestPath-v0")
+            assert bool(e.lib.ge_progress_supported(__import__("ctypes").byref(e.desc))) == (env_id in ("LongestPath-v0", "DistributionCenter-v0"))
         if mode == "compact":    # ge_step_host_compact: one flag byte per env, float32 solution_cost
             h_rew, h_flg, h_cost, h_bits = e.host_io_compact()
         else:

@@ -85,15 +85,19 @@ def test_pdl_chain_on_one_stream_equals_plain():
             assert torch.equal(ref.t[k], env.t[k]), k
 
 
+@pytest.mark.parametrize("cfg", [("LongestPath-v0", 50, 200, {"parenting": 2}, 20 * 1024 - 200),
+                                 ("DistributionCenter-v0", 120, 500, {"parenting": 2, "target_count": 20, "max_distance": 1}, 6 * 1024 - 40)],
+                         ids=["lane", "distcenter"])
 @pytest.mark.parametrize("compact", [False, True], ids=["full", "compact"])
-def test_streamed_host_step_equals_sliced(compact):
+def test_streamed_host_step_equals_sliced(cfg, compact):
     """ge_step_host_pipelined / _compact with chunks = 0 (one step kernel signalling ge_batch.progress + a concurrent write-back kernel
-    that ships every 1024-env chunk as soon as it is complete) delivers exactly what the two-slice path delivers; 20 chunks, ragged tail."""
-    cfg = ("LongestPath-v0", 50, 200, {"parenting": 2}, 20 * 1024 - 200)
+    that ships every 1024-env chunk as soon as it is complete) delivers exactly what the two-slice path delivers; many chunks, ragged tail."""
+    import ctypes
     logs = []
     for chunks in (2, 0):
         e = _make(cfg)
         B = e.B
+        assert e.lib.ge_progress_supported(ctypes.byref(e.desc)) == 1
         if compact:
             h_rew, h_flg, h_cost, h_bits = e.host_io_compact()
         else:
