@@ -545,7 +545,7 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         h_bits.copy_(env.t["mask_bits"])
         torch.cuda.synchronize()
         stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=(args.e2e == "pipelined"),
-                                   chunks=args.e2e_chunks, compact=use_compact)
+                                   chunks=(None if args.e2e_chunks < 0 else args.e2e_chunks), compact=use_compact)
         tot = 0.0
         D.barrier()
         for k in range(3 + Ke):
@@ -567,6 +567,16 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         return envs_all * Ke / D.reduce([tot], "max")[0], stepper, (h_rew, h_flg, h_cost, h_bits)
 
     e2e_val, stepper, (h_rew, h_flg, h_cost, h_bits) = e2e_loop(compact, host_side_policy)
+    e2e_chunks = getattr(stepper, "chunks", args.e2e_chunks)
+    if args.e2e != "pipelined":
+        e2e_how = "ge_step_host: H2D copy of the actions, step kernel, one D2H copy of reward / flags / solution_cost / packed mask, stream sync"
+    elif e2e_chunks > 0:
+        e2e_how = ("ge_step_host_compact / ge_step_host_pipelined: %d slices on one CUDA graph; the step kernels read the int32 actions straight from the "
+                   "pinned host buffer over PCIe (no staging copy), a write-back kernel streams each slice's reward / flags / solution_cost / packed "
+                   "mask into the pinned host arrays while the next slice steps; completion polled" % e2e_chunks)
+    else:
+        e2e_how = ("ge_step_host_compact / ge_step_host_pipelined with chunks = 0: ONE step kernel (actions read from the pinned host buffer) that signals "
+                   "per-1024-env progress counters + a concurrent write-back kernel that ships every chunk as soon as it is complete; completion polled")
     e2e_dev_val = e2e_full_val = None
     if host_side_policy:       # the same call with the actions drawn by the device sampler between calls (untimed): the GPU
         e2e_dev_val = e2e_loop(compact, False)[0]   # does not idle for the milliseconds the numpy policy takes (~10 us per call by itself)
@@ -582,8 +592,8 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
         xbuf = torch.empty((B, N, env.F), dtype=torch.float32, device=dev)
         fused_obs = args.e2e == "pipelined"
         if fused_obs:     # ge_batch.obs_x: every slice's node columns are rewritten on the write-back lane of the SAME call
-            stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True, chunks=args.e2e_chunks, obs_x=xbuf,
-                                       compact=compact)
+            stepper = env.host_stepper(h_act, h_rew, h_flg, h_cost, None, h_bits, stream=side, pipelined=True,
+                                       chunks=(None if args.e2e_chunks < 0 else args.e2e_chunks), obs_x=xbuf, compact=compact)
         t_obs = 0.0
         Ko = max(3, min(Ke, 20))
         for k in range(2 + Ko):
@@ -635,15 +645,10 @@ def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_n
                 "policy": "host numpy policy on the returned mask" if host_side_policy else "device sampler + copy to the pinned action buffer (untimed)",
                 "value_with_device_policy_between_calls": e2e_dev_val,
                 "value_full_result_format": e2e_full_val,
+                "chunks": e2e_chunks,
                 "result_format": ("compact (ge_step_host_compact): reward f32 + 1 flag byte + solution_cost f32 + packed mask" if compact
                                   else "full: reward f32 + 4 flag bytes + solution_cost f64 + packed mask"),
-                "timed": ("sum of the host-step calls on pinned host buffers, " + (
-                    "ge_step_host_compact / ge_step_host_pipelined: %d slices on one CUDA graph; the step kernels read the int32 actions straight from the pinned "
-                    "host buffer over PCIe (no staging copy), a write-back kernel streams each slice's reward / flags / solution_cost / packed "
-                    "mask into the pinned host arrays while the next slice steps; completion polled" % args.e2e_chunks
-                    if args.e2e == "pipelined" else
-                    "ge_step_host: H2D copy of the actions, step kernel, one D2H copy of reward / flags / solution_cost / packed mask, stream sync")
-                    + "; policy between calls untimed")},
+                "timed": "sum of the host-step calls on pinned host buffers, " + e2e_how + "; policy between calls untimed"},
         "e2e_obs": e2e_obs,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms_mean,
@@ -675,7 +680,7 @@ def compact(res):
     r = res["roofline"]
     out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_isolated", "traffic", "kernel", "kernel_ms", "bytes_per_env_step")}
     out["isolated"] = {k: res["isolated"][k] for k in ("value", "ms_per_step", "kernel_ms")}
-    out["e2e"] = {k: res["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "policy")}
+    out["e2e"] = {k: res["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "policy", "chunks")}
     return out
 
 
@@ -882,7 +887,8 @@ def main():
                     help="host result format of the end-to-end step: compact = 1 flag byte + float32 solution_cost per env (ge_step_host_compact)")
     ap.add_argument("--e2e-device-policy", action="store_true",
                     help="headline e2e: draw the actions with the device sampler between calls (untimed) instead of the host numpy policy")
-    ap.add_argument("--e2e-chunks", type=int, default=2, help="slices of the pipelined end-to-end step")
+    ap.add_argument("--e2e-chunks", type=int, default=-1, help="slices of the pipelined end-to-end step; 0 = streamed write-back (one step kernel + "
+                    "concurrent writer fed by progress counters); -1 = auto (streamed for multi-wave batches whose kernel supports it, else 2)")
     ap.add_argument("--no-streaming", action="store_true", help="isolated protocol only (L2 flush + one event pair per step)")
     ap.add_argument("--no-pdl", action="store_true", help="streaming protocol without programmatic dependent launch")
     ap.add_argument("--stream-chunks", type=int, default=0, help="sub-batch chains per step in the streaming protocol (0 = per-workload table)")

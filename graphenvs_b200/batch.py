@@ -494,8 +494,9 @@ class BatchedGraphEnv:
         kernel + a concurrent write-back kernel fed by per-1024-env progress counters (multi-wave batches: 387 vs 486 us per host step at
         1M cfg2 envs; no gain for one-wave batches); chunks=None picks between the two."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
-        if chunks is None:   # auto: multi-wave batches of the lane-per-env families stream their results (chunks = 0), the rest use two slices
-            chunks = 0 if (self.B >= 262144 and self.lib.ge_progress_supported(C.byref(self.desc))) else 2
+        if chunks is None:   # auto: batches of several waves whose kernel signals progress stream their results (chunks = 0), the rest use two slices
+            wave = 148 * 16 * 32 if self.N <= 64 else 148 * 6 * 8          # envs resident at once: lane-per-env tiles / DistributionCenter warps
+            chunks = 0 if (self.B >= 4 * wave and self.lib.ge_progress_supported(C.byref(self.desc))) else 2
         # obs_x: float32[B, N, F] on the device -- the pipelined step also rewrites the observation's node columns, slice by
         # slice on its write-back lane (ge_batch.obs_x); None switches that off again
         assert obs_x is None or (pipelined and obs_x.is_cuda and obs_x.dtype == torch.float32 and obs_x.is_contiguous()
@@ -517,6 +518,7 @@ class BatchedGraphEnv:
         def call():
             check(fn(*args))
         call._keep = keep
+        call.chunks = int(chunks)
         return call
 
     def step_host(self, h_actions, h_reward, h_flags, h_cost, h_mask=None, h_mask_bits=None):
