@@ -360,25 +360,38 @@ def measure_streaming(D, flush, wl, B, K, W, env, env0, args, per_launch_bytes):
             e.step_sampled(SEED, 0)
     torch.cuda.synchronize()
     G = max(g for g in range(1, min(K, 1024) + 1) if K % g == 0)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        if sl:
-            sl[0].fork()
-        for i in range(G):
+    if G < min(K, 64):     # K without a useful divisor (a prime, say): a graph of up to 1000 steps + one graph for the remainder
+        G = min(K, 1000)
+    q, r = divmod(K, G)
+
+    def capture(n, first):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             if sl:
-                sl[i % R].step_sampled(SEED, 0)
-            else:
-                envs[i % R].step_sampled(SEED, 0)
-        if sl:
-            sl[0].join()
+                sl[0].fork()
+            for i in range(first, first + n):
+                if sl:
+                    sl[i % R].step_sampled(SEED, 0)
+                else:
+                    envs[i % R].step_sampled(SEED, 0)
+            if sl:
+                sl[0].join()
+        return g
+
+    graph = capture(G, 0)
+    tail = capture(r, q * G) if r else None
     graph.replay()   # untimed (graph upload)
+    if tail is not None:
+        tail.replay()
     D.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     flush()          # untimed, BEFORE the first event: the first steps start cold too, and while the GPU is busy with it the host
     a.record()       # enqueues the graph behind the event, so the timed region does not begin with the host's launch latency
-    for _ in range(K // G):
+    for _ in range(q):
         graph.replay()
+    if tail is not None:
+        tail.replay()
     b.record()
     D.barrier()
     w1 = time.time()
@@ -387,12 +400,12 @@ def measure_streaming(D, flush, wl, B, K, W, env, env0, args, per_launch_bytes):
     for e in envs:
         e.enable_pdl(False)
     n_launch = K * (len(sl[0].bounds) if sl else 1)
-    del graph, sl, envs
+    del graph, tail, sl, envs
     torch.cuda.empty_cache()
     return {"total_ms": total_ms_max, "ms_per_step": total_ms_max / K, "steps": K, "replicas": R, "chunks": C_, "pdl": not args.no_pdl,
             "gpu_launches": n_launch, "wall": (w0, w1), "rotation_bytes": per_launch_bytes * R,
-            "launch": "CUDA graph of %d steps replayed %d times, ONE event pair around all %d steps; step i runs on batch i %% %d; "
-                      "each step = %d sub-batch launch(es) on %d stream chain(s)%s" % (G, K // G, K, R, C_, C_, ", programmatic dependent launch" if not args.no_pdl else "")}
+            "launch": "CUDA graph of %d steps replayed %d times%s, ONE event pair around all %d steps; step i runs on batch i %% %d; "
+                      "each step = %d sub-batch launch(es) on %d stream chain(s)%s" % (G, q, (" + one graph of %d steps" % r) if r else "", K, R, C_, C_, ", programmatic dependent launch" if not args.no_pdl else "")}
 
 
 def measure_workload(D, flush, wl, B, K, W, args, host_side_policy, envs_total_note=None, sampler=None, seed_env0=None):
